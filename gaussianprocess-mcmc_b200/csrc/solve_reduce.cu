@@ -1,0 +1,145 @@
+// Fused forward substitution + quadratic form + log-determinant:
+//   z = L^-1 g ;  loglik = -( 0.5 * z.z + sum_i log L_ii + 0.5 * n * log(2 pi) )
+//
+// Replaces the reference's log-marginal term (sliceSample.py:122,147; Cholesky/alpha form :120-121,145-146):
+//   -(g^T inv(K_S) g / 2 + log(diag(L_ks^T)).sum() + n*log(2*pi)/2)
+// g^T (L L^T)^-1 g = |L^-1 g|^2, so one triangular solve replaces the dense inverse (or the two
+// solves of solve_chol) and L is read exactly once: 8*n*(n+1)/2 bytes per item, HBM-read bound.
+//
+// One CTA per batch item.  z lives in shared memory; the matrix is walked in block rows of 64:
+// a coalesced GEMV (w = g_R - L[R, :k] z[:k], double2 row reads) followed by a 64x64 triangular
+// solve done by one warp with register-resident w and shuffle broadcasts.
+#include "common.cuh"
+#include "../../include/gpmc.h"
+
+namespace gpmc {
+
+constexpr int SB = 64;                 // block-row height
+constexpr int SBP = SB + 1;            // padded stride of the staged diagonal block
+constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_MAX_N = 16384;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+solve_reduce_kernel(BatchView L, int n, const double *__restrict__ g, int ldg, double *__restrict__ loglik,
+                    const int *__restrict__ info)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int npad = (n + SB - 1) / SB * SB;
+    double *z = sm;                        // [npad]
+    double *D = sm + npad;                 // [SB][SBP] diagonal block
+    double *red = D + SB * SBP;            // [16] reduction scratch
+    const int b = blockIdx.x;
+    if (L.count && b >= *L.count) return;
+    const int m = batch_item(L, b);
+    const double *Lb = L.base + (size_t)m * L.stride;
+    const int ld = L.ld;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (info && info[m] != 0) {
+        if (tid == 0) loglik[m] = nan("");
+        return;
+    }
+    for (int i = tid; i < npad; i += SOLVE_THREADS) z[i] = (i < n) ? g[(size_t)m * ldg + i] : 0.0;
+    __syncthreads();
+
+    double logdet = 0.0;                   // accumulated by warp 0 lanes
+    const int nblk = npad / SB;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int r0 = jb * SB;
+        const int kmax = r0;               // columns [0, kmax) are solved
+        // stage the diagonal block (rows r0.., cols r0..); rows beyond n -> identity
+        for (int e = tid; e < SB * SB; e += SOLVE_THREADS) {
+            const int r = e / SB, c = e - r * SB;
+            double v = 0.0;
+            if (r0 + r < n) { if (c <= r) v = Lb[(size_t)(r0 + r) * ld + r0 + c]; }
+            else if (c == r) v = 1.0;
+            D[r * SBP + c] = v;
+        }
+        // GEMV: each warp owns 8 rows, 4 at a time
+        for (int rr = 0; rr < 8; rr += 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *rowp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + warp * 8 + rr + q;
+                rowp[q] = Lb + (size_t)min(r, n - 1) * ld;
+            }
+            for (int k = 2 * lane; k < kmax; k += 64) {
+                const double2 zz = *reinterpret_cast<const double2 *>(z + k);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 l = *reinterpret_cast<const double2 *>(rowp[q] + k);
+                    acc[q] = fma(l.x, zz.x, acc[q]);
+                    acc[q] = fma(l.y, zz.y, acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double s = warp_sum(acc[q]);
+                const int r = r0 + warp * 8 + rr + q;
+                if (lane == 0 && r < n) z[r] -= s;
+            }
+        }
+        __syncthreads();
+        // 64x64 triangular solve by warp 0; lane holds rows lane and lane+32
+        if (warp == 0) {
+            double w0 = z[r0 + lane], w1 = z[r0 + lane + 32];
+            const double d0 = D[lane * SBP + lane], d1 = D[(lane + 32) * SBP + lane + 32];
+            const double i0 = 1.0 / d0, i1 = 1.0 / d1;
+            if (r0 + lane < n) logdet += log(d0);
+            if (r0 + lane + 32 < n) logdet += log(d1);
+            for (int c = 0; c < 32; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, w0 * i0, c);
+                if (lane == c) w0 = zc;
+                if (lane > c) w0 = fma(-D[lane * SBP + c], zc, w0);
+                w1 = fma(-D[(lane + 32) * SBP + c], zc, w1);
+            }
+            for (int c = 0; c < 32; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, w1 * i1, c);
+                if (lane == c) w1 = zc;
+                if (lane > c) w1 = fma(-D[(lane + 32) * SBP + 32 + c], zc, w1);
+            }
+            z[r0 + lane] = w0;
+            z[r0 + lane + 32] = w1;
+        }
+        __syncthreads();
+    }
+    // quadratic form
+    double q = 0.0;
+    for (int i = tid; i < n; i += SOLVE_THREADS) q = fma(z[i], z[i], q);
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    if (warp == 0) { logdet = warp_sum(logdet); if (lane == 0) red[8] = logdet; }
+    __syncthreads();
+    if (tid == 0) {
+        double qs = 0.0;
+        for (int w = 0; w < SOLVE_THREADS / 32; ++w) qs += red[w];
+        const double log2pi = 1.8378770664093453;      // log(2*pi)
+        loglik[m] = -(qs / 2.0 + red[8] + n * log2pi / 2.0);
+    }
+}
+
+int launch_solve_reduce(BatchView L, int n, const double *g, int ldg, double *loglik, const int *info,
+                        double *zbuf, int B, cudaStream_t s)
+{
+    (void)zbuf;
+    if (B <= 0) return 0;
+    if (n > SOLVE_MAX_N) { set_error("solve_reduce: n=%d exceeds %d", n, SOLVE_MAX_N); return GPMC_EINVAL; }
+    const int npad = (n + SB - 1) / SB * SB;
+    const int smem = (npad + SB * SBP + 16) * (int)sizeof(double);
+    GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    prof_begin(KC_SOLVE, s);
+    solve_reduce_kernel<<<B, SOLVE_THREADS, smem, s>>>(L, n, g, ldg, loglik, info);
+    prof_end(KC_SOLVE, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace gpmc

@@ -1,0 +1,185 @@
+"""Torch-tensor level wrappers over the C ABI: device memory and streams come from PyTorch,
+the arithmetic is libgpmc's hand-written sm_100a kernels."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (KIND_SE_ISO, KIND_SE_ARD, ASM_ADD_S, ASM_LOWER_ONLY, JITTER_NONE, JITTER_PYGPS,
+                   OP_POTRF, OP_LOGLIK, GpmcError)
+
+
+def _stream_ptr(torch):
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f64_cuda(torch, a, name):
+    t = torch.as_tensor(a)
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if not t.is_cuda:
+        t = t.cuda()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def kind_of(D, P):
+    if P == 3:
+        return KIND_SE_ISO
+    if P == D + 2:
+        return KIND_SE_ARD
+    raise ValueError('hyp has %d columns; expected 3 (iso) or D+2=%d (ARD)' % (P, D + 2))
+
+
+class Workspace(object):
+    """Caller-owned device scratch, grown on demand and reused across calls."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, torch, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
+        return self.buf
+
+
+_default_ws = Workspace()
+
+
+def cov_assemble(x, hyp, add_S=False, lower_only=False, jitter=None, out=None, ld=None):
+    """Batched K (or K+S) for ``hyp[B,P]`` over inputs ``x[N,D]`` -> ``A[B,N,ld]`` (device tensor).
+
+    Mirrors ``covK.RBF(np.log(ll), np.log(sf)).getCovMatrix(x, mode='train')`` (+ the S diagonal of
+    ``aux_var_model``), ``sliceSample.py:104-105,136-137,183-190``."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    hyp = _f64_cuda(torch, hyp, 'hyp')
+    if hyp.dim() == 1:
+        hyp = hyp.reshape(1, -1)
+    N, D = x.shape
+    B, P = hyp.shape
+    if ld is None:
+        ld = N + (N & 1)
+    if out is None:
+        out = torch.empty((B, N, ld), dtype=torch.float64, device='cuda')
+        if ld != N:
+            out[:, :, N:] = 0.0
+    jit = None if jitter is None else _f64_cuda(torch, jitter, 'jitter')
+    flags = (ASM_ADD_S if add_S else 0) | (ASM_LOWER_ONLY if lower_only else 0)
+    rc = lib.gpmc_cov_assemble(x.data_ptr(), N, D, hyp.data_ptr(), B, P, kind_of(D, P), flags,
+                               None if jit is None else jit.data_ptr(), out.data_ptr(), ld, _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_cov_assemble')
+    return out
+
+
+def potrf_batched(A, jitter_policy=JITTER_NONE, zero_upper=True, n=None, workspace=None):
+    """In-place batched lower Cholesky of ``A[B,N,ld]`` (device, FP64).  Returns ``info[B]`` (device int32).
+
+    Mirrors ``kcGP.tools.jitchol`` (``sliceSample.py:196,205``)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if not (A.is_cuda and A.dtype == torch.float64 and A.is_contiguous() and A.dim() == 3):
+        raise ValueError('A must be a contiguous CUDA float64 tensor [B, N, ld]')
+    B, N, ld = A.shape
+    if n is not None:
+        N = n
+    info = torch.empty((B,), dtype=torch.int32, device='cuda')
+    need = B * 128 * 128 * 8
+    if jitter_policy == JITTER_PYGPS:
+        need += B * N * ld * 8 + 3 * ((B * 8 + 255) // 256 * 256) + 256
+    ws = (workspace or _default_ws).get(torch, need)
+    rc = lib.gpmc_potrf_batched(A.data_ptr(), N, ld, B, info.data_ptr(), jitter_policy, 1 if zero_upper else 0,
+                                ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_potrf_batched')
+    return info
+
+
+def loglik_batched(x, g, hyp, jitter_policy=JITTER_PYGPS, workspace=None, max_wave=None):
+    """``loglik[b] = log N(g_b; 0, K(hyp_b) + S(hyp_b))`` for device tensors; returns ``(loglik[B], info[B])``.
+
+    The metric's unit (``sliceSample.py:136-137,183-190,196,147``), B items in waves."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    g = _f64_cuda(torch, g, 'g')
+    hyp = _f64_cuda(torch, hyp, 'hyp')
+    if g.dim() == 1:
+        g = g.reshape(1, -1)
+    if hyp.dim() == 1:
+        hyp = hyp.reshape(1, -1)
+    N, D = x.shape
+    B, P = hyp.shape
+    if g.shape != (B, N):
+        raise ValueError('g must be [B=%d, N=%d], got %s' % (B, N, tuple(g.shape)))
+    out = torch.empty((B,), dtype=torch.float64, device='cuda')
+    info = torch.empty((B,), dtype=torch.int32, device='cuda')
+    if B == 0:
+        return out, info
+    need = lib.gpmc_workspace_bytes(OP_LOGLIK, N, D, B if max_wave is None else min(B, max_wave))
+    if max_wave is None:
+        free, _ = torch.cuda.mem_get_info()
+        have = 0 if (workspace or _default_ws).buf is None else (workspace or _default_ws).buf.numel()
+        one = lib.gpmc_workspace_bytes(OP_LOGLIK, N, D, 1)
+        need = max(one, min(need, (free + have) * 6 // 10))
+    ws = (workspace or _default_ws).get(torch, need)
+    rc = lib.gpmc_loglik_batched(x.data_ptr(), N, D, g.data_ptr(), hyp.data_ptr(), B, P, kind_of(D, P), jitter_policy,
+                                 out.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_loglik_batched')
+    return out, info
+
+
+def loglik_host(x, g, hyp, jitter_policy=JITTER_PYGPS):
+    """Same unit for numpy inputs through the library's own pinned staging + stream (the end-to-end call)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    g = np.ascontiguousarray(np.atleast_2d(g), dtype=np.float64)
+    hyp = np.ascontiguousarray(np.atleast_2d(hyp), dtype=np.float64)
+    N, D = x.shape
+    B, P = hyp.shape
+    if g.shape[0] == 0:
+        g = g.reshape(0, N)
+    if g.shape != (B, N):
+        raise ValueError('g must be [B=%d, N=%d], got %s' % (B, N, g.shape))
+    out = np.empty(B, dtype=np.float64)
+    info = np.empty(B, dtype=np.int32)
+    if B == 0:
+        return out, info
+    rc = lib.gpmc_loglik_host(x.ctypes.data, N, D, g.ctypes.data, hyp.ctypes.data, B, P, kind_of(D, P), jitter_policy,
+                              out.ctypes.data, info.ctypes.data)
+    _lib.check(rc, 'gpmc_loglik_host')
+    return out, info
+
+
+def fp64_peak(which='dmma', iters=4096):
+    _lib.require_cuda()
+    lib = _lib.load()
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.gpmc_bench_fp64_peak(0 if which == 'dmma' else 1, iters, ctypes.byref(tf), ctypes.byref(ms)), 'gpmc_bench_fp64_peak')
+    return tf.value, ms.value
+
+
+def profile(on):
+    lib = _lib.load()
+    lib.gpmc_profile_reset()
+    lib.gpmc_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{class name: (total_ms, launches)} of the library's own kernels since the last reset."""
+    lib = _lib.load()
+    out = {}
+    for k, name in enumerate(_lib.KC_NAMES):
+        ms, n = ctypes.c_double(), ctypes.c_longlong()
+        _lib.check(lib.gpmc_profile_read(k, ctypes.byref(ms), ctypes.byref(n)), 'gpmc_profile_read')
+        out[name] = (ms.value, n.value)
+    return out

@@ -1,0 +1,129 @@
+/*
+ * gpmc.h -- C ABI of libgpmc.so: the B200 (sm_100a) implementation of the GP
+ * log-marginal-likelihood hot path of t-kychen/GaussianProcess-MCMC.
+ *
+ * The reference has no FFI: its boundary is the Python call
+ * kcMCMC/sliceSample.py:76  surrogate_slice_sampling(f, x, y, hyp, scale, iter)
+ * and, below it, the kcGP primitives imported at sliceSample.py:13.  Each entry
+ * point here states the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *  - every array is FP64 (IEEE double), C order (row-major), as numpy gives the
+ *    reference; `ld` is the leading dimension (elements between row starts).
+ *  - pointers named *_dev are DEVICE pointers, *_host are HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - return value: 0 on success, a cudaError_t (>0) on a CUDA failure, or a
+ *    negative GPMC_E* code for a bad argument.  gpmc_last_error() gives text.
+ *    Nothing is thrown across the ABI.  Numerical status is per item in
+ *    info[b]: 0 ok, k>0 = leading minor k not positive definite (LAPACK dpotrf
+ *    convention), GPMC_INFO_NOT_PD (-1) = the jitchol ladder gave up (the
+ *    reference raises numpy.linalg.LinAlgError there).
+ *  - the caller owns every buffer including workspace, sized by
+ *    gpmc_workspace_bytes().
+ *  - hyper-parameter rows are natural scale, hyp[b] = (ell_1..ell_E, sf, sn)
+ *    with E = 1 (GPMC_KIND_SE_ISO, the reference's covK.RBF) or E = D
+ *    (GPMC_KIND_SE_ARD); P = E + 2.
+ */
+#ifndef GPMC_H
+#define GPMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPMC_VERSION 100
+
+#define GPMC_KIND_SE_ISO 0
+#define GPMC_KIND_SE_ARD 1
+
+/* flags of gpmc_cov_assemble */
+#define GPMC_ASM_ADD_S      1   /* add S_ii (sliceSample.py:184-190) on the diagonal */
+#define GPMC_ASM_LOWER_ONLY 2   /* write only tiles on/below the diagonal (internal fast path) */
+
+/* jitter policies of the Cholesky (kcGP.tools.jitchol semantics) */
+#define GPMC_JITTER_NONE    0   /* one dpotrf attempt, asynchronous, info as LAPACK */
+#define GPMC_JITTER_PYGPS   1   /* pyGPs 1.3.4 ladder: mean(diag)*1e-6*10^k, k<5 (one host sync) */
+
+#define GPMC_INFO_NOT_PD   (-1)
+
+#define GPMC_EINVAL   (-22)
+#define GPMC_ENOMEM   (-12)
+#define GPMC_EALIGN   (-14)
+
+/* workspace query ops */
+#define GPMC_OP_POTRF   1
+#define GPMC_OP_LOGLIK  2
+#define GPMC_OP_SDS     3
+
+int gpmc_version(void);
+const char *gpmc_last_error(void);
+/* sm count, compute capability, total HBM bytes of the current device */
+int gpmc_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
+
+size_t gpmc_workspace_bytes(int op, int N, int D, int B);
+
+/*
+ * Fused covariance assembly.  Replaces
+ *   covK.RBF(np.log(ll), np.log(sf)).getCovMatrix(x, mode='train')   sliceSample.py:104-105,136-137
+ *   S build / K+S                                                     sliceSample.py:183-190,207
+ * A[b] = sf_b^2 * exp(-0.5 * sum_d ((x_id - x_jd)/ell_bd)^2)  (+ S_ii on the diagonal with
+ * GPMC_ASM_ADD_S; + jitter_dev[b] when jitter_dev != NULL).  Full symmetric fill unless
+ * GPMC_ASM_LOWER_ONLY.  x_dev[N,D]; hyp_dev[B,P]; A_dev[B][N][ld], ld >= N, ld even.
+ */
+int gpmc_cov_assemble(const double *x_dev, int N, int D, const double *hyp_dev, int B, int P,
+                      int kind, int flags, const double *jitter_dev,
+                      double *A_dev, int ld, void *stream);
+
+/*
+ * Batched lower Cholesky, in place.  Replaces kcGP.tools.jitchol (pyGPs 1.3.4 tools.jitchol ->
+ * LAPACK dpotrf(lower=1)) at sliceSample.py:196,205.  On return the lower triangle of A[b]
+ * (row-major) holds L with L L^T = A; the strict upper triangle is zeroed when zero_upper != 0
+ * (as jitchol returns it), else left untouched.  With GPMC_JITTER_PYGPS the caller must pass a
+ * workspace from gpmc_workspace_bytes(GPMC_OP_POTRF, ...) (it keeps a copy for the retries).
+ */
+int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int jitter_policy,
+                       int zero_upper, void *ws_dev, size_t ws_bytes, void *stream);
+
+/*
+ * The metric's unit, "one GP log-lik eval", for B (theta, g) pairs: assemble K+S, Cholesky,
+ * forward substitution, quadratic form and log-determinant, never holding more than one N x N
+ * matrix per in-flight item.  Replaces sliceSample.py:136-137 + :183-190 + :196 + :147 (and the
+ * same at :104-105,:122):
+ *   loglik[b] = -( 0.5 * g_b^T (K_b+S_b)^-1 g_b + sum_i log L_ii + 0.5 * N * log(2 pi) )
+ * g_dev[B,N]; hyp_dev[B,P]; loglik_dev[B]; info_dev[B].  A failed item (info != 0 after the
+ * ladder) gets loglik = NaN, which the sampler treats as a rejected proposal
+ * (sliceSample.py:154).  Items are processed in waves sized to the workspace.
+ */
+int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, const double *hyp_dev,
+                        int B, int P, int kind, int jitter_policy,
+                        double *loglik_dev, int *info_dev,
+                        void *ws_dev, size_t ws_bytes, void *stream);
+
+/*
+ * Same unit with HOST buffers (what a numpy caller holds): pinned staging, H2D of (x, g, hyp),
+ * the device path above, D2H of (loglik, info), all on an internal stream; blocking.
+ * This is the call bench.py times for `e2e`.
+ */
+int gpmc_loglik_host(const double *x_host, int N, int D, const double *g_host, const double *hyp_host,
+                     int B, int P, int kind, int jitter_policy, double *loglik_host, int *info_host);
+
+/* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
+ * register-resident DMMA (mma.sync m8n8k4 f64) and DFMA loops over the whole chip. */
+int gpmc_bench_fp64_peak(int which /*0 = DMMA, 1 = DFMA*/, int iters, double *tflops_out, double *ms_out);
+
+/* Timing hooks: the library records CUDA-event durations of its own kernels per class
+ * (0 assemble, 1 trailing/left update GEMM, 2 panel potf2, 3 panel trsm, 4 solve+reduce)
+ * when enabled; used by bench.py for roofline.achieved. */
+int gpmc_profile_enable(int on);
+int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches);
+int gpmc_profile_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMC_H */
