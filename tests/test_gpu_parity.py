@@ -48,7 +48,9 @@ def test_cov_assemble_ard(gp, so, n, d):
     for b in range(3):
         K = so.cov_matrix(x, H[b])
         KS = K + np.diag(so.s_diagonal(np.diagonal(K), H[b, -1]))
-        np.testing.assert_allclose(A[b], KS, rtol=4e-15, atol=1e-300)
+        # D > 1: scipy's cdist may sum the D squares in another order (1 ulp of the squared distance s),
+        # which exp() turns into a relative 1.1e-16 * s/2 of K; s <= ~1400 before K underflows.
+        np.testing.assert_allclose(A[b], KS, rtol=2e-13, atol=1e-300)
 
 
 def test_cov_assemble_lower_only_and_jitter(gp, so):
@@ -59,7 +61,9 @@ def test_cov_assemble_lower_only_and_jitter(gp, so):
     A = gp.ops.cov_assemble(x, H, add_S=True, lower_only=True, jitter=jit).cpu().numpy()[0, :, :n]
     K = so.cov_matrix(x, H[0])
     KS = K + np.diag(so.s_diagonal(np.diagonal(K), 1.0)) + 0.125 * np.eye(n)
-    np.testing.assert_allclose(np.tril(A), np.tril(KS), rtol=4e-15)
+    err = np.abs(np.tril(A) - np.tril(KS))
+    print('lower_only/jitter max abs err', err.max(), 'at', np.unravel_index(err.argmax(), err.shape))
+    np.testing.assert_allclose(np.tril(A), np.tril(KS), rtol=4e-15, atol=1e-300)
 
 
 # ------------------------------------------------------------------ K3 batched Cholesky
@@ -130,8 +134,10 @@ def _check_rows(gp, rows, ard=False):
         ref_c, ref_i, cond = float(r['ll_chol']), float(r['ll_inv']), float(r['cond'])
         rel_c = abs(ll[0] - ref_c) / abs(ref_c)
         rel_i = abs(ll[0] - ref_i) / abs(ref_i)
-        # Cholesky form (sliceSample.py:145-146): 1e-10 while the problem itself is resolved to 1e-10
-        assert rel_c < RTOL_LOGLIK * max(1.0, cond / 1e7), (r['hyp'], cond, rel_c)
+        # Cholesky form (sliceSample.py:145-146): 1e-10 relative while cond(K+S) <= ~1e6; beyond that no two
+        # FP64 evaluation orders agree to 1e-10 (the reference's own two forms differ by 2.4e-9 at cond 3e8),
+        # so the bound becomes the conditioning limit 0.5 * eps * cond.
+        assert rel_c < max(RTOL_LOGLIK, 1.1e-16 * cond), (r['hyp'], cond, rel_c)
         # literal inv form (:147): 1e-10 up to cond ~1e7; beyond that the reference's own two forms
         # disagree by more than 1e-10 (recorded in the fixture), so allow that gap
         gap = abs(ref_i - ref_c) / abs(ref_c)
@@ -228,8 +234,12 @@ def test_loglik_edge_cases(gp, so):
     assert info[1] == 0 and abs(ll[1] - ref1) <= RTOL_LOGLIK * abs(ref1)
     # sf = 0: K = 0, S = NaN -> the reference's jitchol raises LinAlgError; here info = -1 and NaN (rejected)
     assert info[2] == -1 and np.isnan(ll[2])
-    with pytest.raises(np.linalg.LinAlgError):
-        so.loglik_unit(x, g, H[2])
+    # (the oracle either raises LinAlgError, as LAPACK's dpotrf flags a NaN pivot, or -- with OpenBLAS's own
+    #  potrf, which does not -- returns NaN; both are a rejected proposal at sliceSample.py:154)
+    try:
+        assert np.isnan(so.loglik_unit(x, g, H[2]))
+    except np.linalg.LinAlgError:
+        pass
     # N = 1
     ll, info = gp.ops.loglik_host(np.zeros((1, 1)), np.array([[0.7]]), np.array([[1., 2., 0.5]]))
     assert abs(ll[0] - so.loglik_unit(np.zeros((1, 1)), np.array([0.7]), np.array([1., 2., 0.5]))) < 1e-13
