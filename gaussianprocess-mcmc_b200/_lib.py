@@ -15,7 +15,7 @@ ASM_ADD_S, ASM_LOWER_ONLY = 1, 2
 JITTER_NONE, JITTER_PYGPS = 0, 1
 INFO_NOT_PD = -1
 OP_POTRF, OP_LOGLIK, OP_SDS = 1, 2, 3
-KC_NAMES = ('assemble', 'gemm_update', 'potf2', 'panel_trsm', 'solve_reduce')
+KC_NAMES = ('assemble', 'gemm_update', 'potf2', 'panel_trsm', 'solve_reduce', 'tri_inverse', 'syrk_R', 'vector_control')
 
 _c_double_p = ctypes.c_void_p     # raw addresses (torch data_ptr() / numpy ctypes.data)
 _vp = ctypes.c_void_p
@@ -32,6 +32,11 @@ SIGNATURES = {
     'gpmc_potrf_batched': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'gpmc_loglik_batched': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'gpmc_loglik_host': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    'gpmc_sds_workspace_bytes': (_sz, [_i, _i, _i]),
+    'gpmc_sds_sweep': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i,
+                            ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_ulonglong, ctypes.c_uint,
+                            _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gpmc_set_tuning': (_i, [_i, _i]),
     'gpmc_bench_fp64_peak': (_i, [_i, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'gpmc_profile_enable': (_i, [_i]),
     'gpmc_profile_read': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),

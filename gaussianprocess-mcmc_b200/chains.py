@@ -1,0 +1,145 @@
+"""Many independent SDS chains on one or more B200s.
+
+The reference runs ONE chain (``framework.py:59-77``: ``for i in range(iters): propF, propHyp =
+surrogate_slice_sampling(...)``).  Chains share nothing but the read-only data ``(x, y)``, so an ensemble of B
+chains is the same loop with a batch dimension: the whole transition of every chain is one call into
+``gpmc_sds_sweep``.  With ``torch.distributed`` initialised, chains are sharded contiguously over ranks (chain c on
+rank ``c // (B / world)``), every rank sweeps only its shard, and the per-chain samples ``[theta, loglik, ntrips]``
+are all-gathered once per sweep -- the only collective on the path.  RNG streams are keyed by GLOBAL chain
+id, so the samples do not depend on the number of ranks.
+"""
+import numpy as np
+
+from . import ops
+
+
+def shard_bounds(n_chains, world, rank):
+    """Contiguous shard ``[lo, hi)`` of rank ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n_chains, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ChainEnsemble(object):
+    """B chains of the surrogate-data slice sampler over shared data ``(x, y)``.
+
+    ``F0[B,N]``/``Hyp0[B,P]`` are the GLOBAL initial states (every rank passes the same arrays, or only its shard
+    with ``sharded_input=True``); ``sweep(it)`` advances every local chain by one transition and returns the gathered
+    ``(Hyp[B,P], loglik[B], ntrips[B])`` as numpy arrays on every rank."""
+
+    def __init__(self, x, y, F0, Hyp0, scale, seed=0, max_trips=64, sweeper=None, gather_f=False, sharded_input=False):
+        self.x = np.asarray(x, dtype=np.float64)
+        if self.x.ndim == 1:
+            self.x = self.x.reshape(-1, 1)
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.my = float(np.mean(self.y))                       # sliceSample.py:102
+        self.scale = np.asarray(scale, dtype=np.float64).reshape(-1)
+        self.seed, self.max_trips, self.gather_f = int(seed), int(max_trips), gather_f
+        self.dist = None
+        self.rank, self.world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        F0 = np.asarray(F0, dtype=np.float64)
+        Hyp0 = np.asarray(Hyp0, dtype=np.float64)
+        if sharded_input:
+            self.n_local = Hyp0.shape[0]
+            counts = self._all_counts(self.n_local)
+            self.n_chains = int(sum(counts))
+            self.lo = int(sum(counts[:self.rank]))
+            self.hi = self.lo + self.n_local
+            self._counts = counts
+        else:
+            self.n_chains = Hyp0.shape[0]
+            self.lo, self.hi = shard_bounds(self.n_chains, self.world, self.rank)
+            self.n_local = self.hi - self.lo
+            self._counts = [shard_bounds(self.n_chains, self.world, r)[1] - shard_bounds(self.n_chains, self.world, r)[0]
+                            for r in range(self.world)]
+            F0, Hyp0 = F0[self.lo:self.hi], Hyp0[self.lo:self.hi]
+        self.P = Hyp0.shape[1]
+        # the sweeper is the device path; tests of the host logic inject their own (gloo, no GPU)
+        self._sweeper = sweeper or _DeviceSweeper(self)
+        self._sweeper.load(F0, Hyp0)
+
+    def _all_counts(self, n_local):
+        if self.dist is None:
+            return [n_local]
+        import torch
+        t = torch.zeros(self.world, dtype=torch.int64)
+        t[self.rank] = n_local
+        if self.dist.get_backend() == 'nccl':
+            t = t.cuda()
+        self.dist.all_reduce(t)
+        return [int(v) for v in t.cpu().tolist()]
+
+    def sweep(self, it):
+        """One transition of every chain at MCMC iteration ``it``; returns gathered ``(Hyp, loglik, ntrips)``."""
+        hyp, ll, nt = self._sweeper.sweep(it)                  # local shard, [n_local, ...] tensors/arrays
+        return self._gather(hyp, ll, nt)
+
+    def local_state(self):
+        return self._sweeper.state()
+
+    def _gather(self, hyp, ll, nt):
+        import torch
+        P = self.P
+        pack = torch.cat([torch.as_tensor(hyp, dtype=torch.float64).reshape(self.n_local, P),
+                          torch.as_tensor(ll, dtype=torch.float64).reshape(self.n_local, 1),
+                          torch.as_tensor(nt).to(torch.float64).reshape(self.n_local, 1)], dim=1)
+        if self.dist is None:
+            out = pack
+        else:
+            # ONE all-gather of [theta, loglik, ntrips] per sweep; shards may differ by one chain, so pad to the max
+            mx = max(self._counts)
+            buf = torch.zeros((mx, P + 2), dtype=torch.float64, device=pack.device)
+            buf[:self.n_local] = pack
+            full = torch.empty((self.world * mx, P + 2), dtype=torch.float64, device=pack.device)
+            self.dist.all_gather_into_tensor(full, buf)
+            out = torch.cat([full[r * mx: r * mx + c] for r, c in enumerate(self._counts)], dim=0)
+        out = out.cpu().numpy()
+        return out[:, :P].copy(), out[:, P].copy(), out[:, P + 1].astype(np.int64)
+
+    def run(self, iters, start_iter=0, thin_f=0):
+        """The caller loop of ``framework.py:68-75`` for the ensemble: returns ``histHyp[B, P, iters]``,
+        ``histLL[B, iters]``, ``trips[B, iters]`` (and the local ``histF[n_local, N, kept]`` when ``thin_f > 0``)."""
+        B, P = self.n_chains, self.P
+        histHyp = np.zeros((B, P, iters))
+        histLL = np.zeros((B, iters))
+        trips = np.zeros((B, iters), dtype=np.int64)
+        keepF = []
+        for i in range(iters):
+            h, ll, nt = self.sweep(start_iter + i)
+            histHyp[:, :, i], histLL[:, i], trips[:, i] = h, ll, nt
+            if thin_f and (i % thin_f == 0):
+                keepF.append(self.local_state()[0])
+        if thin_f:
+            return histHyp, histLL, trips, np.stack(keepF, axis=-1)
+        return histHyp, histLL, trips
+
+
+class _DeviceSweeper(object):
+    """Holds the shard's chain state in HBM and advances it with ``gpmc_sds_sweep``."""
+
+    def __init__(self, ens):
+        self.ens = ens
+
+    def load(self, F0, Hyp0):
+        import torch
+        self.torch = torch
+        self.F = torch.tensor(np.ascontiguousarray(F0)).cuda()
+        self.H = torch.tensor(np.ascontiguousarray(Hyp0)).cuda()
+        self.x = torch.tensor(self.ens.x).cuda()
+        self.y = torch.tensor(self.ens.y).cuda()
+        self.scale = torch.tensor(self.ens.scale).cuda()
+
+    def sweep(self, it):
+        e = self.ens
+        nt, ll, status = ops.sds_sweep(self.x, self.y, self.F, self.H, self.scale, it, my=e.my, seed=e.seed,
+                                       chain0=e.lo, max_trips=e.max_trips)
+        return self.H, ll, nt
+
+    def state(self):
+        return self.F.cpu().numpy(), self.H.cpu().numpy()

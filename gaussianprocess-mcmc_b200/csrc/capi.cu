@@ -1,5 +1,6 @@
 // C ABI of libgpmc.so (declared in include/gpmc.h) and the host-side drivers that sequence the kernels.
 #include "common.cuh"
+#include "sequences.cuh"
 #include "../../include/gpmc.h"
 
 #include <stdarg.h>
@@ -23,7 +24,7 @@ void set_error(const char *fmt, ...)
 struct EventPair { cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<EventPair> g_pool[KC_COUNT];
-static size_t g_used[KC_COUNT] = {0, 0, 0, 0, 0};
+static size_t g_used[KC_COUNT] = {};
 
 void prof_begin(int kc, cudaStream_t s)
 {
@@ -44,47 +45,6 @@ void prof_end(int kc, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------ small kernels
-__global__ void zero_upper_kernel(BatchView A, int n)
-{
-    const int b = blockIdx.z;
-    if (A.count && b >= *A.count) return;
-    const int m = batch_item(A, b);
-    double *Ab = A.base + (size_t)m * A.stride;
-    const int r = blockIdx.y * blockDim.y + threadIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n && c < n && c > r) Ab[(size_t)r * A.ld + c] = 0.0;
-}
-
-__global__ void fill_int_kernel(int *p, int v, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-// diag statistics for the jitchol ladder of gpmc_potrf_batched: mean(diag) and any(diag <= 0)
-__global__ void diag_stats_kernel(BatchView A, int n, double *mean_out, int *nonpos_out)
-{
-    const int m = blockIdx.x;
-    const double *Ab = A.base + (size_t)m * A.stride;
-    __shared__ double ssum[256];
-    __shared__ int sbad[256];
-    double s = 0.0;
-    int bad = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double d = Ab[(size_t)i * A.ld + i];
-        s += d;
-        bad |= (d <= 0.0);
-    }
-    ssum[threadIdx.x] = s;
-    sbad[threadIdx.x] = bad;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; sbad[threadIdx.x] |= sbad[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { mean_out[m] = ssum[0] / n; nonpos_out[m] = sbad[0]; }
-}
-
 // restore item map[b] from the backup copy and add jitter[map[b]] to its diagonal
 __global__ void restore_jitter_kernel(BatchView A, const double *backup, int n, const double *jitter)
 {
@@ -101,46 +61,6 @@ __global__ void restore_jitter_kernel(BatchView A, const double *backup, int n, 
     }
 }
 
-// ------------------------------------------------------------------ blocked Cholesky sequencing
-// Left-looking by block columns of NB: update the block column with everything to its left (DMMA GEMM),
-// factor the diagonal block (+ inverse), turn the rows below into L with one more DMMA GEMM.
-static int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, int zero_upper,
-                          cudaStream_t s)
-{
-    const int nt = (n + NB - 1) / NB;
-    for (int j = 0; j < nt; ++j) {
-        const int j0 = j * NB;
-        const int width = std::min(NB, n - j0);
-        if (j > 0) {
-            GemmArgs g;
-            g.A = A; g.W = nullptr; g.strideW = 0; g.n = n;
-            g.r0 = j0; g.rows = n - j0; g.c0 = j0; g.cols = width;
-            g.k0 = 0; g.klen = j0; g.lower_only = 0; g.mode = 0;
-            int rc = launch_gemm(g, B, s);
-            if (rc) return rc;
-        }
-        int rc = launch_potf2(A, n, j0, W, strideW, info, zero_upper, B, s);
-        if (rc) return rc;
-        if (j0 + NB < n) {
-            GemmArgs g;
-            g.A = A; g.W = W; g.strideW = strideW; g.n = n;
-            g.r0 = j0 + NB; g.rows = n - j0 - NB; g.c0 = j0; g.cols = NB;
-            g.k0 = 0; g.klen = NB; g.lower_only = 0; g.mode = 1;
-            rc = launch_gemm(g, B, s);
-            if (rc) return rc;
-        }
-    }
-    if (zero_upper) {
-        dim3 blk(32, 8);
-        dim3 grid((n + 31) / 32, (n + 7) / 8, B);
-        zero_upper_kernel<<<grid, blk, 0, s>>>(A, n);
-        GPMC_LAUNCH_CHECK();
-    }
-    return 0;
-}
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline int ld_for(int n) { return (n + 15) / 16 * 16; }
 
 // S_ii and K_ii + S_ii on the host (same expression order as the kernel / sliceSample.py:185-190),
 // used only to size the jitter of the ladder.
@@ -241,10 +161,9 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     char *wp = (char *)ws_dev;
     double *W = (double *)wp; wp += wbytes;
     BatchView A{A_dev, (long long)N * ld, ld, nullptr, nullptr};
-    fill_int_kernel<<<(B + 255) / 256, 256, 0, s>>>(info_dev, 0, B);
-    GPMC_LAUNCH_CHECK();
+    { int rc0 = fill_int(info_dev, 0, B, s); if (rc0) return rc0; }
 
-    if (jitter_policy != GPMC_JITTER_PYGPS) return potrf_sequence(A, N, B, info_dev, W, NB * NB, zero_upper, s);
+    if (jitter_policy != GPMC_JITTER_PYGPS) return potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s);
 
     // pyGPs jitchol: keep a copy, try once, then the jitter ladder on the items that failed.
     double *backup = (double *)wp; wp += mat_bytes;
@@ -252,7 +171,7 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     double *jit_dev = (double *)wp; wp += align_up((size_t)B * sizeof(double), 256);
     int *map_dev = (int *)wp;
     GPMC_CUDA_CHECK(cudaMemcpyAsync(backup, A_dev, mat_bytes, cudaMemcpyDeviceToDevice, s));
-    int rc = potrf_sequence(A, N, B, info_dev, W, NB * NB, zero_upper, s);
+    int rc = potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s);
     if (rc) return rc;
     std::vector<int> info(B);
     GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -265,7 +184,7 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     BatchView Bk{backup, (long long)N * ld, ld, nullptr, nullptr};
     int *bad_dev = nullptr;
     GPMC_CUDA_CHECK(cudaMalloc(&bad_dev, B * sizeof(int)));
-    diag_stats_kernel<<<B, 256, 0, s>>>(Bk, N, mean_dev, bad_dev);
+    { int rc0 = diag_stats(Bk, N, mean_dev, bad_dev, B, s); if (rc0) return rc0; }
     std::vector<double> mean(B);
     std::vector<int> bad(B);
     GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), mean_dev, B * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -286,7 +205,7 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
         restore_jitter_kernel<<<dim3(64, nf), 256, 0, s>>>(Am, backup, N, jit_dev);
         for (int i : todo) info[i] = 0;
         GPMC_CUDA_CHECK(cudaMemcpyAsync(info_dev, info.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
-        rc = potrf_sequence(Am, N, nf, info_dev, W, NB * NB, zero_upper, s);
+        rc = potrf_sequence(Am, N, nf, info_dev, W, NB * NB, 0, zero_upper, s);
         if (rc) return rc;
         GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s));
         GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -322,8 +241,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
     double *mats = (double *)wp;
     double *W = (double *)(wp + (size_t)wave * l.mat_elems * sizeof(double));
 
-    fill_int_kernel<<<(B + 255) / 256, 256, 0, s>>>(info_dev, 0, B);
-    GPMC_LAUNCH_CHECK();
+    { int rc0 = fill_int(info_dev, 0, B, s); if (rc0) return rc0; }
     std::vector<double> hyp_host;
     for (int s0 = 0; s0 < B; s0 += wave) {
         const int nb = std::min(wave, B - s0);
@@ -333,7 +251,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
         BatchView A{mats, (long long)l.mat_elems, l.ld, nullptr, nullptr};
         int rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A, nb, s);
         if (rc) return rc;
-        rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, s);
+        rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s);
         if (rc) return rc;
         if (jitter_policy == GPMC_JITTER_PYGPS) {
             std::vector<int> info(nb);
@@ -362,7 +280,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                     BatchView Am{mats, (long long)l.mat_elems, l.ld, map_dev, nullptr};
                     rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, jit_dev, Am, nf, s);
                     if (rc) return rc;
-                    rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, s);
+                    rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s);
                     if (rc) return rc;
                     GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
                     GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -375,7 +293,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                 GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
             }
         }
-        rc = launch_solve_reduce(A, N, g_w, N, loglik_dev + s0, info_w, nullptr, nb, s);
+        rc = launch_solve_reduce(A, N, g_w, nullptr, N, nullptr, loglik_dev + s0, info_w, nb, s);
         if (rc) return rc;
     }
     return 0;
@@ -449,6 +367,12 @@ int gpmc_bench_fp64_peak(int which, int iters, double *tflops_out, double *ms_ou
     if (tflops_out) *tflops_out = tf;
     if (ms_out) *ms_out = ms;
     return rc;
+}
+
+int gpmc_set_tuning(int key, int value)
+{
+    if (key == 0) { set_gemm_config(value); return 0; }
+    return GPMC_EINVAL;
 }
 
 int gpmc_profile_enable(int on) { g_prof_on = (on != 0); return 0; }

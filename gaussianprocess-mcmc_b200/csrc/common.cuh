@@ -11,7 +11,7 @@ constexpr int NB = 128;            // panel width / tile edge of the blocked Cho
 constexpr int MAX_ELL = 8;         // max number of length-scales (ARD input dimension)
 
 // kernel classes for the profiling hooks (gpmc_profile_read)
-enum KernelClass { KC_ASSEMBLE = 0, KC_GEMM = 1, KC_POTF2 = 2, KC_TRSM = 3, KC_SOLVE = 4, KC_COUNT = 5 };
+enum KernelClass { KC_ASSEMBLE = 0, KC_GEMM = 1, KC_POTF2 = 2, KC_TRSM = 3, KC_SOLVE = 4, KC_INV = 5, KC_SYRK_R = 6, KC_VEC = 7, KC_COUNT = 8 };
 
 void set_error(const char *fmt, ...);
 void prof_begin(int kc, cudaStream_t s);
@@ -57,29 +57,48 @@ __device__ __forceinline__ int batch_item(const BatchView &v, int b) { return v.
 int launch_cov_assemble(const double *x, int N, int D, const double *hyp, int P, int n_ell, int flags,
                         const double *jitter, BatchView A, int B, cudaStream_t s);
 
-// gemm_dmma.cu
-//   mode 0: C[r0+i][c0+j] -= sum_k A[r0+i][k0+k] * A[c0+j][k0+k]      (left-looking / trailing update)
-//   mode 1: C[r0+i][c0+j]  = sum_k A[r0+i][c0+k] * W[j][k]            (panel TRSM as GEMM with W = L11^-1)
-struct GemmArgs {
-    BatchView A;           // the matrix being factorised
-    const double *W;       // mode 1: per-item [NB][NB] inverse of the diagonal block (row-major, dense)
-    long long strideW;
-    int n;                 // matrix order (rows/cols valid)
-    int r0, rows;          // output rows [r0, r0+rows)
-    int c0, cols;          // output cols [c0, c0+cols)   (cols <= NB in mode 1)
-    int k0, klen;          // contraction range (multiple of 16)
-    int lower_only;        // skip tiles strictly above the diagonal (r-tile < c-tile), SYRK use
-    int mode;
+// gemm_dmma.cu :  C[i][j] (op)= sum_k A[i][k] * B[j][k]   ("NT": both operands K-contiguous, row-major)
+struct Operand {
+    const double *base;    // first matrix
+    long long stride;      // elements between matrices of consecutive batch items
+    int ld;
 };
-int launch_gemm(const GemmArgs &a, int B, cudaStream_t s);
+enum Epilogue {
+    EPI_SUB = 0,           // C = C - acc            (Cholesky update)
+    EPI_SET = 1,           // C = acc                (panel TRSM via inverse; Y = U L^T)
+    EPI_NEGSET = 2,        // C = -acc               (block column of U = L^-T)
+    EPI_R = 3              // C = S - S acc S (+1e-11 on the diagonal), S = diag(svec)   (posterior covariance R)
+};
+struct GemmArgs {
+    BatchView C;           // output matrices; its map/count select the batch items of the launch
+    Operand A, B;          // A rows <-> output rows, B rows <-> output cols (indexed by the same mapped item)
+    int cr0, cc0;          // output origin (row, col) in C
+    int rows, cols;        // output extent
+    int ar0, br0;          // operand rows corresponding to cr0 / cc0
+    int k0, bk0;           // first contraction column in A / in B
+    int klen;              // contraction length (the tail beyond a multiple of 16 must be zero-padded in memory)
+    int lower_only;        // enumerate only tiles with tile-row >= tile-col (square output, SYRK use)
+    int k_follow_row;      // A (and B) are upper triangular in (row, k): start k at the tile's first A row
+    int epi;               // Epilogue
+    const double *svec;    // EPI_R: per-item diagonal of S, [N]
+    long long stride_s;
+};
+int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s);
+void set_gemm_config(int cfg);
 
 // potf2.cu : factor the NB x NB diagonal block at (j0, j0) in place, write its inverse to W
 int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                  int B, cudaStream_t s);
 
-// solve_reduce.cu : z = L^-1 g, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)
-int launch_solve_reduce(BatchView L, int n, const double *g, int ldg, double *loglik, const int *info,
-                        double *zbuf, int B, cudaStream_t s);
+// solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)
+//   a, b, zout are per-item vectors with row stride ldv (b, zout, loglik may be nullptr)
+int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, int ldv, double *zout,
+                        double *loglik, const int *info, int B, cudaStream_t s);
+// trmv.cu : out = T x (+ add) for a triangular row-major T;  upper=0: lower triangle, upper=1: upper triangle.
+//   mode 0: out = T x + add            (f' = C eta + m, sliceSample.py:140)
+//   mode 1: out = add - svec * (T x)   (m = g - S (K+S)^-1 g with T = L^-T, x = L^-1 g; sliceSample.py:204)
+int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const double *add, const double *svec,
+                int ldv, double *out, int B, cudaStream_t s);
 
 // microbench.cu
 int run_fp64_peak(int which, int iters, double *tflops, double *ms);

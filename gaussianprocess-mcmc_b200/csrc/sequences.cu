@@ -1,0 +1,223 @@
+// Host-side sequencing of the batched kernels: blocked Cholesky, triangular inverse, posterior covariance.
+#include "sequences.cuh"
+#include "../../include/gpmc.h"
+
+#include <algorithm>
+
+namespace gpmc {
+
+// ------------------------------------------------------------------------------ small kernels
+__global__ void zero_upper_kernel(BatchView A, int n)
+{
+    const int b = blockIdx.z;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    double *Ab = A.base + (size_t)m * A.stride;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && c < n && c > r) Ab[(size_t)r * A.ld + c] = 0.0;
+}
+
+__global__ void fill_int_kernel(int *p, int v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void fill_int_mapped_kernel(int *p, int v, const int *map, const int *count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count) p[map[i]] = v;
+}
+
+__global__ void add_diag_kernel(BatchView A, int n, const double *jitter)
+{
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A.base[(size_t)m * A.stride + (size_t)i * A.ld + i] += jitter[m];
+}
+
+// mean(diag) and any(diag <= 0) per item -- inputs of the jitchol ladder
+__global__ void diag_stats_kernel(BatchView A, int n, double *mean_out, int *nonpos_out)
+{
+    const int b = blockIdx.x;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const double *Ab = A.base + (size_t)m * A.stride;
+    __shared__ double ssum[256];
+    __shared__ int sbad[256];
+    double s = 0.0;
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = Ab[(size_t)i * A.ld + i];
+        s += d;
+        bad |= (d <= 0.0);
+    }
+    ssum[threadIdx.x] = s;
+    sbad[threadIdx.x] = bad;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; sbad[threadIdx.x] |= sbad[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { mean_out[m] = ssum[0] / n; nonpos_out[m] = sbad[0]; }
+}
+
+// U_ii = (L_ii^-1)^T: upper triangular diagonal block with explicit zeros below the diagonal
+__global__ void __launch_bounds__(256) write_diag_block_T_kernel(BatchView A, int n, int i0, const double *W, long long strideW)
+{
+    const int b = blockIdx.x;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    __shared__ double tile[32][33];
+    double *Ab = A.base + (size_t)m * A.stride;
+    const double *Wb = W + (size_t)m * strideW;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int br = 0; br < NB; br += 32) {
+        for (int bc = 0; bc < NB; bc += 32) {
+            // tile of U at (br, bc) = transpose of the tile of W at (bc, br)
+            for (int r = ty; r < 32; r += 8) tile[r][tx] = Wb[(bc + r) * NB + br + tx];
+            __syncthreads();
+            for (int r = ty; r < 32; r += 8) {
+                const int gr = i0 + br + r, gc = i0 + bc + tx;
+                if (gr < n && gc < n) Ab[(size_t)gr * A.ld + gc] = (bc + tx >= br + r) ? tile[tx][r] : 0.0;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void copy_rows_kernel(double *dst, int ldd, const double *src, int lds, int n)
+{
+    const int r = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[(size_t)r * ldd + i] = src[(size_t)r * lds + i];
+}
+
+int fill_int(int *p, int v, int n, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, v, n);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int fill_int_mapped(int *p, int v, const int *map, const int *count, int nmax, cudaStream_t s)
+{
+    if (nmax <= 0) return 0;
+    fill_int_mapped_kernel<<<(nmax + 255) / 256, 256, 0, s>>>(p, v, map, count);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int add_diag(BatchView A, int n, const double *jitter, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    add_diag_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(A, n, jitter);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int diag_stats(BatchView A, int n, double *mean_out, int *nonpos_out, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    diag_stats_kernel<<<B, 256, 0, s>>>(A, n, mean_out, nonpos_out);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows, cudaStream_t s)
+{
+    if (rows <= 0) return 0;
+    copy_rows_kernel<<<dim3(std::max(1, std::min(8, (n + 255) / 256)), rows), 256, 0, s>>>(dst, ldd, src, lds, n);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ blocked Cholesky sequencing
+// Left-looking by block columns of NB: update the block column with everything to its left (DMMA GEMM),
+// factor the diagonal block (+ inverse), turn the rows below into L with one more DMMA GEMM.
+int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
+                   int zero_upper, cudaStream_t s)
+{
+    const int nt = (n + NB - 1) / NB;
+    const Operand self{A.base, A.stride, A.ld};
+    for (int j = 0; j < nt; ++j) {
+        const int j0 = j * NB;
+        const int width = std::min(NB, n - j0);
+        double *Wj = W + (size_t)j * w_step;
+        if (j > 0) {
+            GemmArgs g{};
+            g.C = A; g.A = self; g.B = self;
+            g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
+            g.ar0 = j0; g.br0 = j0; g.k0 = 0; g.bk0 = 0; g.klen = j0;
+            g.epi = EPI_SUB;
+            int rc = launch_gemm(g, B, KC_GEMM, s);
+            if (rc) return rc;
+        }
+        int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper, B, s);
+        if (rc) return rc;
+        if (j0 + NB < n) {
+            GemmArgs g{};
+            g.C = A; g.A = self; g.B = Operand{Wj, strideW, NB};
+            g.cr0 = j0 + NB; g.cc0 = j0; g.rows = n - j0 - NB; g.cols = NB;
+            g.ar0 = j0 + NB; g.br0 = 0; g.k0 = j0; g.bk0 = 0; g.klen = NB;
+            g.epi = EPI_SET;
+            rc = launch_gemm(g, B, KC_TRSM, s);
+            if (rc) return rc;
+        }
+    }
+    if (zero_upper) {
+        dim3 blk(32, 8);
+        dim3 grid((n + 31) / 32, (n + 7) / 8, B);
+        zero_upper_kernel<<<grid, blk, 0, s>>>(A, n);
+        GPMC_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// U = L^-T, built block column by block column in the upper triangle of the same buffer:
+//   U[0:i0, i] = -(U[0:i0, 0:i0] L[i, 0:i0]^T) (L_ii^-1)^T ,   U[i, i] = (L_ii^-1)^T
+// (the k < row part of U is zero, so every tile starts its contraction at its own first row).
+int inverse_sequence(BatchView A, int n, int B, const double *W, long long strideW, cudaStream_t s)
+{
+    const int nt = (n + NB - 1) / NB;
+    const Operand self{A.base, A.stride, A.ld};
+    for (int i = 0; i < nt; ++i) {
+        const int i0 = i * NB;
+        const int width = std::min(NB, n - i0);
+        const double *Wi = W + (size_t)i * NB * NB;
+        if (i > 0) {
+            GemmArgs g{};
+            g.C = A; g.A = self; g.B = self;
+            g.cr0 = 0; g.cc0 = i0; g.rows = i0; g.cols = width;
+            g.ar0 = 0; g.br0 = i0; g.k0 = 0; g.bk0 = 0; g.klen = i0;
+            g.k_follow_row = 1;
+            g.epi = EPI_SET;
+            int rc = launch_gemm(g, B, KC_INV, s);
+            if (rc) return rc;
+            GemmArgs h{};
+            h.C = A; h.A = self; h.B = Operand{Wi, strideW, NB};
+            h.cr0 = 0; h.cc0 = i0; h.rows = i0; h.cols = width;
+            h.ar0 = 0; h.br0 = 0; h.k0 = i0; h.bk0 = 0; h.klen = (width + 15) & ~15;   // stays inside ld (pads are zero)
+            h.epi = EPI_NEGSET;
+            rc = launch_gemm(h, B, KC_INV, s);
+            if (rc) return rc;
+        }
+        prof_begin(KC_INV, s);
+        write_diag_block_T_kernel<<<B, 256, 0, s>>>(A, n, i0, Wi, strideW);
+        prof_end(KC_INV, s);
+        GPMC_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int r_sequence(BatchView Rm, BatchView U, int n, int B, const double *svec, long long stride_s, cudaStream_t s)
+{
+    GemmArgs g{};
+    g.C = Rm; g.A = Operand{U.base, U.stride, U.ld}; g.B = g.A;
+    g.cr0 = 0; g.cc0 = 0; g.rows = n; g.cols = n;
+    g.ar0 = 0; g.br0 = 0; g.k0 = 0; g.bk0 = 0; g.klen = n;
+    g.lower_only = 1; g.k_follow_row = 1;
+    g.epi = EPI_R; g.svec = svec; g.stride_s = stride_s;
+    return launch_gemm(g, B, KC_SYRK_R, s);
+}
+
+}  // namespace gpmc

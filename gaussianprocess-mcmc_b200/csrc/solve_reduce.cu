@@ -1,5 +1,6 @@
 // Fused forward substitution + quadratic form + log-determinant:
-//   z = L^-1 g ;  loglik = -( 0.5 * z.z + sum_i log L_ii + 0.5 * n * log(2 pi) )
+//   z = L^-1 (a - b) ;  loglik = -( 0.5 * z.z + sum_i log L_ii + 0.5 * n * log(2 pi) )
+// (also used for the whitening eta = C^-1 (f - m), sliceSample.py:108, with loglik = nullptr)
 //
 // Replaces the reference's log-marginal term (sliceSample.py:122,147; Cholesky/alpha form :120-121,145-146):
 //   -(g^T inv(K_S) g / 2 + log(diag(L_ks^T)).sum() + n*log(2*pi)/2)
@@ -27,8 +28,8 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
-solve_reduce_kernel(BatchView L, int n, const double *__restrict__ g, int ldg, double *__restrict__ loglik,
-                    const int *__restrict__ info)
+solve_reduce_kernel(BatchView L, int n, const double *__restrict__ va, const double *__restrict__ vb, int ldv,
+                    double *__restrict__ zout, double *__restrict__ loglik, const int *__restrict__ info)
 {
     extern __shared__ __align__(16) double sm[];
     const int npad = (n + SB - 1) / SB * SB;
@@ -43,10 +44,15 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ g, int ldg, d
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (info && info[m] != 0) {
-        if (tid == 0) loglik[m] = nan("");
+        if (tid == 0 && loglik) loglik[m] = nan("");
+        if (zout) for (int i = tid; i < n; i += SOLVE_THREADS) zout[(size_t)m * ldv + i] = nan("");
         return;
     }
-    for (int i = tid; i < npad; i += SOLVE_THREADS) z[i] = (i < n) ? g[(size_t)m * ldg + i] : 0.0;
+    for (int i = tid; i < npad; i += SOLVE_THREADS) {
+        double v = 0.0;
+        if (i < n) { v = va[(size_t)m * ldv + i]; if (vb) v -= vb[(size_t)m * ldv + i]; }
+        z[i] = v;
+    }
     __syncthreads();
 
     double logdet = 0.0;                   // accumulated by warp 0 lanes
@@ -111,6 +117,8 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ g, int ldg, d
         }
         __syncthreads();
     }
+    if (zout) for (int i = tid; i < n; i += SOLVE_THREADS) zout[(size_t)m * ldv + i] = z[i];
+    if (!loglik) return;
     // quadratic form
     double q = 0.0;
     for (int i = tid; i < n; i += SOLVE_THREADS) q = fma(z[i], z[i], q);
@@ -126,17 +134,16 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ g, int ldg, d
     }
 }
 
-int launch_solve_reduce(BatchView L, int n, const double *g, int ldg, double *loglik, const int *info,
-                        double *zbuf, int B, cudaStream_t s)
+int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, int ldv, double *zout,
+                        double *loglik, const int *info, int B, cudaStream_t s)
 {
-    (void)zbuf;
     if (B <= 0) return 0;
     if (n > SOLVE_MAX_N) { set_error("solve_reduce: n=%d exceeds %d", n, SOLVE_MAX_N); return GPMC_EINVAL; }
     const int npad = (n + SB - 1) / SB * SB;
     const int smem = (npad + SB * SBP + 16) * (int)sizeof(double);
     GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     prof_begin(KC_SOLVE, s);
-    solve_reduce_kernel<<<B, SOLVE_THREADS, smem, s>>>(L, n, g, ldg, loglik, info);
+    solve_reduce_kernel<<<B, SOLVE_THREADS, smem, s>>>(L, n, a, b, ldv, zout, loglik, info);
     prof_end(KC_SOLVE, s);
     GPMC_LAUNCH_CHECK();
     return 0;

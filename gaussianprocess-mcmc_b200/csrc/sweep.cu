@@ -1,0 +1,330 @@
+// gpmc_sds_sweep: one surrogate-data slice-sampling transition (kcMCMC/sliceSample.py:76-163) for B chains,
+// with the hyper-parameter shrink loop resident on the device.
+//
+// Per evaluation of the auxiliary model at theta (aux_var_model, sliceSample.py:165-207, plus the log-marginal
+// :122/:147) the device does, for every active chain at once:
+//     K+S (lower)            cov_assemble                                  :136-137,183-190
+//     L = chol(K+S)          potrf_sequence (+ pyGPs jitter ladder)        :196
+//     z = L^-1 g, log N(g)   solve_reduce                                  :147
+//     U = L^-T               inverse_sequence
+//     m = g - S (U z)        trmv (upper)        == R S^-1 g               :204
+//     R = S - S (U U^T) S    r_sequence          == K - V^T V, V = L^-1 K  :197-198   (+1e-11 I, :205)
+//     C = chol(R + 1e-11 I)  potrf_sequence (+ ladder)                     :205
+// R is formed in its algebraically reduced form: K - K (K+S)^-1 K = S - S (K+S)^-1 S for diagonal S.  It is the
+// same matrix with less cancellation (entries of size S instead of differences of entries of size sf^2) and
+// 4/3 N^3 flops per proposal instead of 8/3 N^3 ("SDS proposal").
+#include "common.cuh"
+#include "sequences.cuh"
+#include "sds.cuh"
+#include "../../include/gpmc.h"
+
+#include <algorithm>
+#include <vector>
+#include <math.h>
+
+namespace gpmc {
+
+struct SweepBuffers {
+    int n, ld, ldv, P, nt, cap;                  // cap = chains per wave
+    double *buf1, *buf2, *Wsave, *Wtmp;
+    double *Fin, *Fout, *g, *svec, *fprop, *z, *m, *eta;          // [cap, ldv]
+    double *theta, *hyp_min, *hyp_max, *hyp_in, *hyp_out;         // [cap, P]
+    double *G, *log_u0, *threshold, *cur_llk, *curG, *last_prop, *last_llk, *jit, *mean, *loglik_out;   // [cap]
+    int *done, *ntrips, *map, *count, *info1, *info2, *bad, *fmap;   // ints
+};
+
+static char *carve(char *&p, size_t bytes) { char *r = p; p += align_up(bytes, 256); return r; }
+
+static void layout(SweepBuffers &w, char *p, int n, int P, int cap)
+{
+    w.n = n; w.ld = ld_for(n); w.ldv = w.ld; w.P = P; w.nt = (n + NB - 1) / NB; w.cap = cap;
+    const size_t mat = (size_t)n * w.ld * 8;
+    w.buf1 = (double *)carve(p, mat * cap);
+    w.buf2 = (double *)carve(p, mat * cap);
+    w.Wsave = (double *)carve(p, (size_t)w.nt * NB * NB * 8 * cap);
+    w.Wtmp = (double *)carve(p, (size_t)NB * NB * 8 * cap);
+    double **vecs[] = {&w.Fin, &w.Fout, &w.g, &w.svec, &w.fprop, &w.z, &w.m, &w.eta};
+    for (double **v : vecs) *v = (double *)carve(p, (size_t)w.ldv * 8 * cap);
+    double **hyps[] = {&w.theta, &w.hyp_min, &w.hyp_max, &w.hyp_in, &w.hyp_out};
+    for (double **v : hyps) *v = (double *)carve(p, (size_t)P * 8 * cap);
+    double **scal[] = {&w.G, &w.log_u0, &w.threshold, &w.cur_llk, &w.curG, &w.last_prop, &w.last_llk, &w.jit, &w.mean, &w.loglik_out};
+    for (double **v : scal) *v = (double *)carve(p, (size_t)8 * cap);
+    int **ints[] = {&w.done, &w.ntrips, &w.map, &w.info1, &w.info2, &w.bad, &w.fmap};
+    for (int **v : ints) *v = (int *)carve(p, (size_t)4 * cap);
+    w.count = (int *)carve(p, 256);
+}
+
+static size_t sweep_bytes(int n, int P, int cap)
+{
+    // the carve arithmetic of layout(), replayed without a base pointer
+    const int ld = ld_for(n), nt = (n + NB - 1) / NB;
+    const size_t mat = (size_t)n * ld * 8;
+    size_t tot = 0;
+    auto add = [&](size_t b) { tot += align_up(b, 256); };
+    add(mat * cap); add(mat * cap); add((size_t)nt * NB * NB * 8 * cap); add((size_t)NB * NB * 8 * cap);
+    for (int i = 0; i < 8; ++i) add((size_t)ld * 8 * cap);
+    for (int i = 0; i < 5; ++i) add((size_t)P * 8 * cap);
+    for (int i = 0; i < 10; ++i) add((size_t)8 * cap);
+    for (int i = 0; i < 7; ++i) add((size_t)4 * cap);
+    add(256);
+    return tot + 256;
+}
+
+// S_ii and diag(K+S) on the host (sliceSample.py:185-190 expression order), used only to size the ladder's jitter
+static double host_diag_value(const double *h, int P)
+{
+    const double sf = h[P - 2], sn = h[P - 1];
+    const double sf2 = exp(2.0 * log(sf));
+    const double kinv = 1.0 / sf2;
+    const double v1 = 1.0 / (sn * sn) + kinv;
+    double Sii = 1.0 / (v1 - kinv);
+    if (Sii < 0.0) Sii = 0.0;
+    return sf2 + Sii;
+}
+
+struct AuxCtx {
+    const double *x; int N, D, P, n_ell;
+    SweepBuffers *w;
+    cudaStream_t s;
+    int jitter_policy;
+};
+
+// Read info[] of the currently active chains and return the wave-local ids that failed.
+static int failed_items(const AuxCtx &c, const int *info_dev, const std::vector<int> &active, std::vector<int> &failed,
+                        std::vector<int> &info_host)
+{
+    info_host.resize(c.w->cap);
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info_host.data(), info_dev, c.w->cap * sizeof(int), cudaMemcpyDeviceToHost, c.s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    failed.clear();
+    for (int id : active) if (info_host[id] != 0) failed.push_back(id);
+    return 0;
+}
+
+// Mark wave-local chains as "jitchol gave up" (the reference raises LinAlgError; here the proposal is rejected).
+static int mark_not_pd(const AuxCtx &c, int *info_dev, const std::vector<int> &ids)
+{
+    if (ids.empty()) return 0;
+    std::vector<int> marks(c.w->cap, 0);
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(marks.data(), info_dev, c.w->cap * 4, cudaMemcpyDeviceToHost, c.s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    for (int id : ids) marks[id] = GPMC_INFO_NOT_PD;
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info_dev, marks.data(), c.w->cap * 4, cudaMemcpyHostToDevice, c.s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    return 0;
+}
+
+// Evaluate the auxiliary model at w.theta for the chains listed in `active` (w.map/w.count hold the same list).
+static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
+{
+    SweepBuffers &w = *c.w;
+    cudaStream_t s = c.s;
+    const int na = (int)active.size();
+    if (na == 0) return 0;
+    const long long mat = (long long)w.n * w.ld;
+    BatchView A1{w.buf1, mat, w.ld, w.map, w.count};
+    BatchView A2{w.buf2, mat, w.ld, w.map, w.count};
+    const long long strideW = (long long)w.nt * NB * NB;
+    int rc;
+    // ---- K+S and its Cholesky factor (jitchol, :196)
+    if ((rc = fill_int_mapped(w.info1, 0, w.map, w.count, na, s))) return rc;
+    if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A1, na, s))) return rc;
+    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s))) return rc;
+    if (c.jitter_policy == GPMC_JITTER_PYGPS) {
+        std::vector<int> failed, info;
+        if ((rc = failed_items(c, w.info1, active, failed, info))) return rc;
+        if (!failed.empty()) {
+            std::vector<double> th((size_t)w.cap * c.P), jit(w.cap, 0.0);
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(th.data(), w.theta, th.size() * 8, cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+            std::vector<int> todo, hopeless;
+            for (int id : failed) {
+                const double dv = host_diag_value(&th[(size_t)id * c.P], c.P);
+                if (dv <= 0.0) hopeless.push_back(id);              // any(diag <= 0): LinAlgError
+                else { jit[id] = dv * 1e-6; todo.push_back(id); }   // (NaN diag lands here and keeps failing)
+            }
+            int *cnt = w.count + 16;         // scratch count next to the main one (same 256-byte slot)
+            for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
+                const int nf = (int)todo.size();
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
+                BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+                if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
+                if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, w.jit, F1, nf, s))) return rc;
+                if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s))) return rc;
+                std::vector<int> still, info2;
+                if ((rc = failed_items(c, w.info1, todo, still, info2))) return rc;
+                for (int id : still) jit[id] *= 10.0;
+                todo.swap(still);
+            }
+            // "not positive definite, even with jitter"
+            hopeless.insert(hopeless.end(), todo.begin(), todo.end());
+            if ((rc = mark_not_pd(c, w.info1, hopeless))) return rc;
+        }
+    }
+    // ---- z = L^-1 g and the log marginal (:147)
+    if ((rc = launch_solve_reduce(A1, w.n, w.g, nullptr, w.ldv, w.z, w.G, w.info1, na, s))) return rc;
+    // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
+    if ((rc = inverse_sequence(A1, w.n, na, w.Wsave, strideW, s))) return rc;
+    if ((rc = launch_trmv(A1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, na, s))) return rc;
+    if ((rc = r_sequence(A2, A1, w.n, na, w.svec, w.ldv, s))) return rc;
+    // ---- C = chol(R + 1e-11 I) (jitchol, :205)
+    if ((rc = fill_int_mapped(w.info2, 0, w.map, w.count, na, s))) return rc;
+    if ((rc = potrf_sequence(A2, w.n, na, w.info2, w.Wtmp, NB * NB, 0, 0, s))) return rc;
+    if (c.jitter_policy == GPMC_JITTER_PYGPS) {
+        std::vector<int> failed, info;
+        if ((rc = failed_items(c, w.info2, active, failed, info))) return rc;
+        // chains whose K+S already failed carry NaN everywhere: nothing to retry
+        std::vector<int> info1;
+        if (!failed.empty()) {
+            info1.resize(w.cap);
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(info1.data(), w.info1, w.cap * 4, cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+            std::vector<int> todo;
+            for (int id : failed) if (info1[id] == 0) todo.push_back(id);
+            int *cnt = w.count + 16;
+            std::vector<double> jit(w.cap, 0.0), mean(w.cap, 0.0);
+            std::vector<int> bad(w.cap, 0);
+            bool first = true;
+            for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
+                const int nf = (int)todo.size();
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
+                BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+                BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
+                if ((rc = r_sequence(F2, F1, w.n, nf, w.svec, w.ldv, s))) return rc;      // rebuild R + 1e-11 I
+                if (first) {
+                    if ((rc = diag_stats(F2, w.n, w.mean, w.bad, nf, s))) return rc;
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), w.mean, w.cap * 8, cudaMemcpyDeviceToHost, s));
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(bad.data(), w.bad, w.cap * 4, cudaMemcpyDeviceToHost, s));
+                    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+                    std::vector<int> keep;
+                    for (int id : todo) { if (!bad[id]) { jit[id] = mean[id] * 1e-6; keep.push_back(id); } }
+                    first = false;
+                    if (keep.size() != todo.size()) { todo.swap(keep); --attempt; continue; }
+                }
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
+                if ((rc = add_diag(F2, w.n, w.jit, nf, s))) return rc;
+                if ((rc = fill_int_mapped(w.info2, 0, w.fmap, cnt, nf, s))) return rc;
+                if ((rc = potrf_sequence(F2, w.n, nf, w.info2, w.Wtmp, NB * NB, 0, 0, s))) return rc;
+                std::vector<int> still, tmp;
+                if ((rc = failed_items(c, w.info2, todo, still, tmp))) return rc;
+                for (int id : still) jit[id] *= 10.0;
+                todo.swap(still);
+            }
+            if ((rc = mark_not_pd(c, w.info2, todo))) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace gpmc
+
+using namespace gpmc;
+
+extern "C" {
+
+size_t gpmc_sds_workspace_bytes(int N, int P, int chains_per_wave)
+{
+    if (N <= 0 || P < 3 || chains_per_wave <= 0) return 0;
+    return sweep_bytes(N, P, chains_per_wave);
+}
+
+int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, double *hyp_dev, int B, int P,
+                   int kind, const double *scale_dev, const double *prior_k_dev, const double *prior_theta_dev, int iter,
+                   double my, double lower, double upper, unsigned long long seed, unsigned chain0,
+                   const double *tape_z, const double *tape_v, const double *tape_u0, const double *tape_U, int tape_trips,
+                   int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
+                   void *ws_dev, size_t ws_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
+    if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2 || max_trips <= 0) {
+        set_error("sds_sweep: bad shape N=%d D=%d B=%d P=%d kind=%d max_trips=%d", N, D, B, P, kind, max_trips);
+        return GPMC_EINVAL;
+    }
+    if (tape_U && tape_trips < 1) { set_error("sds_sweep: tape_U given with tape_trips=%d", tape_trips); return GPMC_EINVAL; }
+    if (B == 0) return 0;
+    // chains per wave from the workspace
+    int cap = B;
+    while (cap > 1 && sweep_bytes(N, P, cap) > ws_bytes) cap = (cap + 1) / 2;
+    if (!ws_dev || sweep_bytes(N, P, cap) > ws_bytes) {
+        set_error("sds_sweep: workspace %zu bytes cannot hold one chain (%zu needed)", ws_bytes, sweep_bytes(N, P, 1));
+        return GPMC_ENOMEM;
+    }
+    SweepBuffers w;
+    layout(w, (char *)ws_dev, N, P, cap);
+    // pad columns of the matrices must be zero (the DMMA kernels contract over multiples of 16)
+    if (w.ld != N) {
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)N * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)N * cap, s));
+    }
+    AuxCtx ctx{x_dev, N, D, P, n_ell, &w, s, jitter_policy};
+    std::vector<int> active;
+    for (int c0 = 0; c0 < B; c0 += cap) {
+        const int nb = std::min(cap, B - c0);
+        // stage the wave's state into stride-ldv rows
+        int rc;
+        if ((rc = copy_rows(w.Fin, w.ldv, F_dev + (size_t)c0 * N, N, N, nb, s))) return rc;
+        if ((rc = copy_rows(w.Fout, w.ldv, F_dev + (size_t)c0 * N, N, N, nb, s))) return rc;
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(w.hyp_in, hyp_dev + (size_t)c0 * P, (size_t)nb * P * 8, cudaMemcpyDeviceToDevice, s));
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(w.hyp_out, hyp_dev + (size_t)c0 * P, (size_t)nb * P * 8, cudaMemcpyDeviceToDevice, s));
+
+        SdsState st{};
+        st.n = N; st.P = P; st.ldv = w.ldv; st.iter = iter; st.sweep = (unsigned)iter; st.chain0 = chain0 + (unsigned)c0; st.seed = seed;
+        st.my = my; st.lower = lower; st.upper = upper;
+        st.y = y_dev; st.scale = scale_dev; st.prior_k = prior_k_dev; st.prior_theta = prior_theta_dev;
+        st.F = w.Fin; st.hyp = w.hyp_in; st.F_out = w.Fout; st.hyp_out = w.hyp_out; st.loglik_out = w.loglik_out;
+        st.g = w.g; st.svec = w.svec; st.fprop = w.fprop; st.theta = w.theta; st.hyp_min = w.hyp_min; st.hyp_max = w.hyp_max;
+        st.G = w.G; st.log_u0 = w.log_u0; st.threshold = w.threshold; st.cur_llk = w.cur_llk; st.curG = w.curG;
+        st.last_proposal = w.last_prop; st.last_llk = w.last_llk;
+        st.done = w.done; st.ntrips = w.ntrips; st.map = w.map; st.count = w.count;
+        st.tape_z = tape_z ? tape_z + (size_t)c0 * N : nullptr;
+        st.tape_v = tape_v ? tape_v + (size_t)c0 * P : nullptr;
+        st.tape_u0 = tape_u0 ? tape_u0 + c0 : nullptr;
+        st.tape_U = tape_U ? tape_U + (size_t)c0 * tape_trips * P : nullptr;
+        st.tape_trips = tape_trips;
+
+        // ---- current state: g, bracket, aux model at theta, whitening, threshold (:102-129)
+        if ((rc = launch_sds_begin(st, nb, s))) return rc;
+        active.resize(nb);
+        for (int i = 0; i < nb; ++i) active[i] = i;
+        if ((rc = aux_eval(ctx, active))) return rc;
+        BatchView C2{w.buf2, (long long)N * w.ld, w.ld, w.map, w.count};
+        if ((rc = launch_solve_reduce(C2, N, w.Fin, w.m, w.ldv, w.eta, nullptr, w.info2, nb, s))) return rc;     // eta, :108
+        if ((rc = launch_sds_threshold(st, nb, s))) return rc;
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(w.loglik_out, w.G, (size_t)nb * 8, cudaMemcpyDeviceToDevice, s));
+
+        // ---- shrink loop (:131-163): device decides, host only learns how many chains remain
+        const int trips_allowed = tape_U ? std::min(max_trips, tape_trips) : max_trips;
+        std::vector<int> done(nb);
+        for (int trip = 0; trip < trips_allowed && !active.empty(); ++trip) {
+            const int na = (int)active.size();
+            if ((rc = launch_sds_propose(st, na, trip, s))) return rc;
+            if ((rc = aux_eval(ctx, active))) return rc;
+            if ((rc = launch_trmv(C2, N, 0, 0, w.eta, w.m, nullptr, w.ldv, w.fprop, na, s))) return rc;          // f' = C eta + m, :140
+            if ((rc = launch_sds_accept(st, na, s))) return rc;
+            if ((rc = launch_sds_compact(st, nb, s))) return rc;
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(done.data(), w.done, nb * 4, cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+            active.clear();
+            for (int i = 0; i < nb; ++i) if (!done[i]) active.push_back(i);
+        }
+        // ---- results of the wave
+        if ((rc = copy_rows(F_dev + (size_t)c0 * N, N, w.Fout, w.ldv, N, nb, s))) return rc;
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(hyp_dev + (size_t)c0 * P, w.hyp_out, (size_t)nb * P * 8, cudaMemcpyDeviceToDevice, s));
+        if (ntrips_dev) GPMC_CUDA_CHECK(cudaMemcpyAsync(ntrips_dev + c0, w.ntrips, nb * 4, cudaMemcpyDeviceToDevice, s));
+        if (loglik_dev) GPMC_CUDA_CHECK(cudaMemcpyAsync(loglik_dev + c0, w.loglik_out, nb * 8, cudaMemcpyDeviceToDevice, s));
+        if (status_dev) {
+            // 0 = accepted; 1 = the trip budget ran out (state unchanged)
+            std::vector<int> st_host(nb, 0);
+            for (int id : active) st_host[id] = 1;
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(status_dev + c0, st_host.data(), nb * 4, cudaMemcpyHostToDevice, s));
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

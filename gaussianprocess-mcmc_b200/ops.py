@@ -160,6 +160,91 @@ def loglik_host(x, g, hyp, jitter_policy=JITTER_PYGPS):
     return out, info
 
 
+def prior_constants(n_ell):
+    """Hyper-prior shape/scale for P = n_ell + 2 (``sliceSample.py:124-125``: k = [1, 3, 3], theta = [1, 1.5, 3];
+    every extra ARD length-scale reuses the length-scale entry)."""
+    k = np.array([1.0] * n_ell + [3.0, 3.0])
+    th = np.array([1.0] * n_ell + [1.5, 3.0])
+    return k, th
+
+
+class Tape(object):
+    """Explicit randomness of one sweep for B chains, in the reference's draw order
+    (``sliceSample.py:194,110,127,132``): ``z[B,N]`` N(0,1); ``v[B,P]``, ``u0[B]``, ``U[B,T,P]`` U(0,1)."""
+
+    def __init__(self, z, v, u0, U):
+        self.z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+        self.v = np.ascontiguousarray(np.atleast_2d(v), dtype=np.float64)
+        self.u0 = np.ascontiguousarray(np.atleast_1d(u0), dtype=np.float64)
+        U = np.asarray(U, dtype=np.float64)
+        self.U = np.ascontiguousarray(U[None] if U.ndim == 2 else U)
+
+
+def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max_trips=64, prior_k=None,
+              prior_theta=None, jitter_policy=JITTER_PYGPS, workspace=None, chains_per_wave=None):
+    """One surrogate-data slice-sampling transition for every chain (``sliceSample.py:76-163``), in place.
+
+    ``F[B,N]`` and ``Hyp[B,P]`` are CUDA float64 tensors holding the chains' current ``(f, theta)``; on return
+    they hold the accepted ``(f', theta')``.  Returns ``(ntrips[B], loglik[B], status[B])`` device tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    N, D = x.shape
+    if not (F.is_cuda and F.dtype == torch.float64 and F.is_contiguous() and F.dim() == 2 and F.shape[1] == N):
+        raise ValueError('F must be a contiguous CUDA float64 tensor [B, N]')
+    if not (Hyp.is_cuda and Hyp.dtype == torch.float64 and Hyp.is_contiguous() and Hyp.dim() == 2):
+        raise ValueError('Hyp must be a contiguous CUDA float64 tensor [B, P]')
+    B, P = Hyp.shape
+    if F.shape[0] != B:
+        raise ValueError('F and Hyp disagree on the number of chains')
+    kind = kind_of(D, P)
+    if my is None:
+        my = float(np.mean(np.asarray(y.cpu() if hasattr(y, 'cpu') else y, dtype=np.float64)))      # sliceSample.py:102
+    y = _f64_cuda(torch, y, 'y').reshape(-1)
+    k, th = prior_constants(P - 2)
+    k = _f64_cuda(torch, k if prior_k is None else prior_k, 'prior_k')
+    th = _f64_cuda(torch, th if prior_theta is None else prior_theta, 'prior_theta')
+    scale = _f64_cuda(torch, scale, 'scale').reshape(-1)
+    if scale.numel() != P:
+        raise ValueError('scale must have P=%d entries' % P)
+    ntrips = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    loglik = torch.empty((B,), dtype=torch.float64, device='cuda')
+    status = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    if B == 0:
+        return ntrips, loglik, status
+    tz = tv = tu = tU = None
+    ttrips = 0
+    if tape is not None:
+        if tape.z.shape != (B, N) or tape.v.shape != (B, P) or tape.u0.shape != (B,) or tape.U.shape[0] != B or tape.U.shape[2] != P:
+            raise ValueError('tape shapes do not match B=%d N=%d P=%d' % (B, N, P))
+        tz, tv, tu, tU = (torch.tensor(a).cuda() for a in (tape.z, tape.v, tape.u0, tape.U))
+        ttrips = tape.U.shape[1]
+    wsobj = workspace or _default_ws
+    if chains_per_wave is None:
+        free, _ = torch.cuda.mem_get_info()
+        have = 0 if wsobj.buf is None else wsobj.buf.numel()
+        budget = (free + have) * 6 // 10
+        chains_per_wave = B
+        while chains_per_wave > 1 and lib.gpmc_sds_workspace_bytes(N, P, chains_per_wave) > budget:
+            chains_per_wave = (chains_per_wave + 1) // 2
+    ws = wsobj.get(torch, lib.gpmc_sds_workspace_bytes(N, P, min(B, chains_per_wave)))
+    ptr = lambda t: None if t is None else t.data_ptr()
+    rc = lib.gpmc_sds_sweep(x.data_ptr(), y.data_ptr(), N, D, F.data_ptr(), Hyp.data_ptr(), B, P, kind,
+                            scale.data_ptr(), k.data_ptr(), th.data_ptr(), int(it),
+                            my, 0.0 - my, 100.0 - my, int(seed), int(chain0),
+                            ptr(tz), ptr(tv), ptr(tu), ptr(tU), ttrips, int(max_trips), jitter_policy,
+                            ntrips.data_ptr(), loglik.data_ptr(), status.data_ptr(),
+                            ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_sds_sweep')
+    return ntrips, loglik, status
+
+
+def set_tuning(key, value):
+    _lib.check(_lib.load().gpmc_set_tuning(int(key), int(value)), 'gpmc_set_tuning')
+
+
 def fp64_peak(which='dmma', iters=4096):
     _lib.require_cuda()
     lib = _lib.load()

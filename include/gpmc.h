@@ -112,12 +112,41 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
 int gpmc_loglik_host(const double *x_host, int N, int D, const double *g_host, const double *hyp_host,
                      int B, int P, int kind, int jitter_policy, double *loglik_host, int *info_host);
 
+/*
+ * One surrogate-data slice-sampling transition for B independent chains, shrink loop on the device.
+ * Replaces kcMCMC/sliceSample.py:76-163 (surrogate_slice_sampling) including aux_var_model (:165-207),
+ * log_gamma (:209-232) and likK.TruncatedGauss2.evaluate (:117-118,142-143), i.e. the body of the caller
+ * loops framework.py:68-75 / demoRegression.py:23-30 for many chains at once.
+ *   F_dev[B,N], hyp_dev[B,P]   in: current (f, theta) of every chain; out: the accepted (f', theta')
+ *   scale_dev[P]               slice widths (:110-112); prior_k_dev / prior_theta_dev[P] (:124-125)
+ *   iter                       MCMC iteration: noise frozen and its prior dropped while iter < 500 (:128,133,151)
+ *   my, lower, upper           mean(y), 0 - my, 100 - my (:102,114-115)
+ *   randomness                 tape_* != NULL: explicit draws in the reference's order -- z[B,N] (:194),
+ *                              v[B,P] (:110), u0[B] (:127), U[B,tape_trips,P] (:132), all U(0,1)/N(0,1);
+ *                              else Philox4x32-10 keyed by (seed, chain0 + chain index, iter)
+ *   max_trips                  bound on the shrink loop (the reference's `while True`); a chain that uses it
+ *                              up keeps its state and gets status 1
+ *   ntrips_dev[B], loglik_dev[B] (log N(g;0,K+S) at the returned theta), status_dev[B]  may be NULL
+ * Chains are processed in waves sized to the workspace (gpmc_sds_workspace_bytes(N, P, chains_per_wave)).
+ */
+size_t gpmc_sds_workspace_bytes(int N, int P, int chains_per_wave);
+int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, double *hyp_dev, int B, int P,
+                   int kind, const double *scale_dev, const double *prior_k_dev, const double *prior_theta_dev, int iter,
+                   double my, double lower, double upper, unsigned long long seed, unsigned chain0,
+                   const double *tape_z, const double *tape_v, const double *tape_u0, const double *tape_U, int tape_trips,
+                   int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
+                   void *ws_dev, size_t ws_bytes, void *stream);
+
+/* Kernel tuning knobs for experiments (key 0: DMMA tile kernel variant, 0 = 8 warps 64x32, 1 = 16 warps 32x32). */
+int gpmc_set_tuning(int key, int value);
+
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
  * register-resident DMMA (mma.sync m8n8k4 f64) and DFMA loops over the whole chip. */
 int gpmc_bench_fp64_peak(int which /*0 = DMMA, 1 = DFMA*/, int iters, double *tflops_out, double *ms_out);
 
 /* Timing hooks: the library records CUDA-event durations of its own kernels per class
- * (0 assemble, 1 trailing/left update GEMM, 2 panel potf2, 3 panel trsm, 4 solve+reduce)
+ * (0 assemble, 1 Cholesky update GEMM, 2 panel potf2, 3 panel trsm, 4 solve+reduce, 5 triangular inverse,
+ *  6 posterior-covariance SYRK, 7 vector/control kernels)
  * when enabled; used by bench.py for roofline.achieved. */
 int gpmc_profile_enable(int on);
 int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches);
