@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-peaks', action='store_true')
+    ap.add_argument('--gemm-cfg', type=int, default=None, help='experiment: DMMA tile kernel variant (0: 8 warps, 1: 16 warps)')
     return ap.parse_args()
 
 
@@ -183,6 +184,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if args.gemm_cfg is not None:
+        gp.ops.set_tuning(0, args.gemm_cfg)
     n, B = args.n, args.chains_per_gpu
     x_h = np.arange(n, dtype=np.float64).reshape(n, 1)
     # chains are keyed by GLOBAL id, so the job's inputs do not depend on how it is sharded

@@ -59,8 +59,14 @@ def s_diagonal(Kii, sn):
 
 
 # ------------------------------------------------------------- a3: aux_var_model
-def aux_var_model(f, K, sn, g=None, z=None):
+def aux_var_model(f, K, sn, g=None, z=None, r_form='literal'):
     """``aux_var_model`` (``sliceSample.py:165-207``) with the draw of ``g`` taken from ``z``.
+
+    ``r_form='literal'``: ``R = K - V^T V`` with ``V = solve(L, K)`` exactly as ``:197-198``.
+    ``r_form='reduced'``: the same matrix as ``S - S (K+S)^-1 S`` and ``m = g - S (K+S)^-1 g`` (what the CUDA
+    path evaluates).  ``chol(R + 1e-11 I)`` has condition ~1e11, so the two forms give ``C`` (hence ``f'``) that
+    differ far above rounding; the difference between them is the resolution to which the reference itself
+    defines ``f'`` (see tests/test_gpu_sds.py).
 
     ``:194`` draws ``g ~ N(f, S)`` through ``multivariate_normal`` (an SVD of the diagonal
     S); that equals ``f + sqrt(S_ii) z_i`` with ``z`` in draw order (pinned in make_golden).
@@ -72,10 +78,17 @@ def aux_var_model(f, K, sn, g=None, z=None):
     if g is None:
         g = f + np.sqrt(Sii) * z                               # :194
     L = kcgp_shim.jitchol(K + S)                               # :196
-    V = np.linalg.solve(L, K)                                  # :197
-    R_theta = K - np.dot(V.T, V)                               # :198
-    with np.errstate(divide='ignore', invalid='ignore'):
-        m_theta_g = np.dot(np.dot(R_theta, np.linalg.inv(S)), g)   # :204
+    if r_form == 'literal':
+        V = np.linalg.solve(L, K)                              # :197
+        R_theta = K - np.dot(V.T, V)                           # :198
+        with np.errstate(divide='ignore', invalid='ignore'):
+            m_theta_g = np.dot(np.dot(R_theta, np.linalg.inv(S)), g)   # :204
+    else:
+        U = scipy.linalg.solve_triangular(L, np.eye(n), lower=True).T      # U = L^-T
+        P = np.dot(U, U.T)                                     # (K+S)^-1
+        R_theta = np.diag(Sii) - Sii[:, None] * P * Sii[None, :]
+        zz = scipy.linalg.solve_triangular(L, g, lower=True)
+        m_theta_g = g - Sii * np.dot(U, zz)
     chol_R_theta = kcgp_shim.jitchol(R_theta + np.eye(n) * 1e-11)  # :205
     return g, K + S, m_theta_g, chol_R_theta, L
 
@@ -163,7 +176,7 @@ class SweepTrace(object):
 
 
 def surrogate_slice_sampling(f, x, y, hyp, scale, it, tape, max_trips=None, trace=None,
-                             log_marginal='inv'):
+                             log_marginal='inv', r_form='literal'):
     """One surrogate-data slice-sampling transition, ``sliceSample.py:76-163``, on a tape.
 
     ``tape`` has ``z[N]``, ``v[P]``, ``u0``, ``U[T,P]`` (see ``reference_loader.Tape``).
@@ -177,7 +190,7 @@ def surrogate_slice_sampling(f, x, y, hyp, scale, it, tape, max_trips=None, trac
     n_ell = P - 2
     my = np.mean(y)                                                          # :102
     K = cov_matrix(x, hyp)                                                   # :104-105
-    g, K_S, m_theta_g, chol_R_theta, L_ks = aux_var_model(f, K, hyp[P - 1], z=tape.z)   # :107
+    g, K_S, m_theta_g, chol_R_theta, L_ks = aux_var_model(f, K, hyp[P - 1], z=tape.z, r_form=r_form)   # :107
     ita = np.linalg.solve(chol_R_theta, f - m_theta_g)                       # :108
 
     v = 0. + (scale - 0.) * tape.v                                           # :110
@@ -211,7 +224,7 @@ def surrogate_slice_sampling(f, x, y, hyp, scale, it, tape, max_trips=None, trac
         propG = propG_c = prop_llk = np.nan
         prop_f = None
         try:
-            g, K_S, m_theta_g, chol_R_theta, L_ks = aux_var_model(f, nK, prop_hyp[P - 1], g=g)   # :139
+            g, K_S, m_theta_g, chol_R_theta, L_ks = aux_var_model(f, nK, prop_hyp[P - 1], g=g, r_form=r_form)   # :139
             prop_f = np.dot(chol_R_theta, ita) + m_theta_g                   # :140
             prop_llk = trunc_gauss2_loglik(y - my, prop_f, prop_hyp[P - 1], lower, upper)        # :142-143
             propG = log_marginal_inv_form(g, K_S, L_ks)                      # :147
@@ -241,7 +254,7 @@ def surrogate_slice_sampling(f, x, y, hyp, scale, it, tape, max_trips=None, trac
                 hyp_max[i] = prop_hyp[i]                                     # :162-163
 
 
-def run_chain(x, y, hyp0, scale, iters, seed, f0=None, start_iter=0, max_trips=64):
+def run_chain(x, y, hyp0, scale, iters, seed, f0=None, start_iter=0, max_trips=64, r_form='literal'):
     """The caller loop of ``framework.py:59-77`` / ``demoRegression.py:15-32`` on per-iteration tapes
     (``Tape.from_seed(seed + it)``).  Returns ``(histF[N,iters], histHyp[P,iters], trips[iters])``."""
     from .reference_loader import Tape
@@ -255,7 +268,7 @@ def run_chain(x, y, hyp0, scale, iters, seed, f0=None, start_iter=0, max_trips=6
     for i in range(iters):
         tr = SweepTrace()
         tape = Tape.from_seed(seed + i, n, p=propHyp.shape[0], max_trips=max_trips)
-        propF, propHyp = surrogate_slice_sampling(propF, x, y, propHyp, scale, start_iter + i, tape, trace=tr)
+        propF, propHyp = surrogate_slice_sampling(propF, x, y, propHyp, scale, start_iter + i, tape, trace=tr, r_form=r_form)
         histF[:, i] = propF
         histHyp[:, i] = propHyp
         trips[i] = tr.n_trips
