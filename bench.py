@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=4096, help='observations per chain (BASELINE: 4096)')
+    ap.add_argument('--nobs', dest='n', type=int, default=4096, help='observations per chain (BASELINE: 4096)')
     ap.add_argument('--chains-per-gpu', type=int, default=1024, help='BASELINE config 5: 8192 chains over 8 GPUs')
     ap.add_argument('--cpu-sample', type=int, default=4, help='evals in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
