@@ -38,6 +38,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gpmc_set_tuning': (_i, [_i, _i]),
     'gpmc_bench_fp64_peak': (_i, [_i, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    'gpmc_bench_dmma_ilp': (_i, [_i, _i, _i, ctypes.POINTER(ctypes.c_double)]),
     'gpmc_profile_enable': (_i, [_i]),
     'gpmc_profile_read': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     'gpmc_profile_reset': (_i, []),

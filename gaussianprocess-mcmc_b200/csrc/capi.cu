@@ -369,6 +369,14 @@ int gpmc_bench_fp64_peak(int which, int iters, double *tflops_out, double *ms_ou
     return rc;
 }
 
+int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_out)
+{
+    double tf = 0.0;
+    const int rc = run_dmma_ilp(nacc, warps_per_sm, iters, &tf);
+    if (tflops_out) *tflops_out = tf;
+    return rc;
+}
+
 int gpmc_set_tuning(int key, int value)
 {
     if (key == 0) { set_gemm_config(value); return 0; }

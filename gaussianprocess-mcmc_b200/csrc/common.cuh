@@ -102,5 +102,6 @@ int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const 
 
 // microbench.cu
 int run_fp64_peak(int which, int iters, double *tflops, double *ms);
+int run_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops);
 
 }  // namespace gpmc

@@ -1,30 +1,45 @@
-// Panel kernel of the blocked Cholesky: factor one 128x128 diagonal block in shared memory and
-// produce its inverse in the same sweep.
+// Panel kernel of the blocked Cholesky: factor one 128x128 diagonal block in shared memory and produce its
+// inverse in the same sweep.
 //
-// Part of kcGP.tools.jitchol -> LAPACK dpotrf(lower=1) (sliceSample.py:196,205): the unblocked
-// dpotf2 step on the diagonal block, with LAPACK's failure convention (info = index of the first
-// non-positive / NaN pivot, 1-based, sliceSample's jitchol turns it into a jitter retry).
+// Part of kcGP.tools.jitchol -> LAPACK dpotrf(lower=1) (sliceSample.py:196,205): the dpotf2 step on the diagonal
+// block, with LAPACK's failure convention (info = 1-based index of the first non-positive / NaN pivot; jitchol
+// turns it into a jitter retry).
 //
-// The block is held as one 128x129 array T in shared memory: the lower triangle becomes L11, and the
-// strict upper triangle accumulates X = L11^-T by running the same column operations on an appended
-// identity (rows of [A11; I] are updated alike).  W = L11^-1 is written out dense so the panel TRSM
-// below the block is a DMMA GEMM (mode 1 of gemm_dmma.cu).
+// The block lives in shared memory as ONE 128x132 array T: its lower triangle becomes L11 and its strict upper
+// triangle accumulates X = L11^-T, obtained by running the same block operations on an appended identity (the
+// rows of [A11; I] are updated alike).  Inner blocking is 32:
+//   * the 32x32 diagonal sub-block is factored by ONE WARP, one matrix row (and one identity row) per lane in
+//     registers, pivots and multipliers broadcast with warp shuffles -- no block barrier inside;
+//   * the sub-panel (rows of L below and rows of X above) is multiplied by the inverse of the sub-block and the
+//     trailing sub-blocks are updated with FP64 DMMA (mma.sync.m8n8k4) on fragments read from T.
+// W = L11^-1 is written out dense so the panel TRSM below the block is a DMMA GEMM (gemm_dmma.cu).
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
 
-constexpr int PT = 129;                       // smem row stride (doubles), odd -> conflict-free columns
+constexpr int PT = 132;                       // smem row stride (doubles): 4 mod 16 -> conflict-free DMMA fragments
+constexpr int PB = 32;                        // inner block
+constexpr int PC = 36;                        // row stride of the clean 32x32 inverse
 constexpr int POTF2_THREADS = 256;
-constexpr int POTF2_SMEM = (NB * PT + NB) * (int)sizeof(double);
+constexpr int POTF2_SMEM = (NB * PT + PB * PC + NB) * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma884_p(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info,
                  int zero_upper)
 {
     extern __shared__ __align__(16) double sm[];
-    double *T = sm;                           // [NB][PT]
-    double *dinv = sm + NB * PT;              // 1 / L_kk
+    double *T = sm;                           // [NB][PT]   lower: L, strict upper: X = L^-T
+    double *Lc = sm + NB * PT;                // [PB][PC]   clean inverse of the current 32x32 diagonal sub-block
+    double *dinv = Lc + PB * PC;              // [NB]       1 / L_kk
+    __shared__ int s_fail;
     const int b = blockIdx.x;
     if (A.count && b >= *A.count) return;
     const int m = batch_item(A, b);
@@ -32,8 +47,9 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     const int ld = A.ld;
     const int nv = min(NB, n - j0);           // valid order of this block
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;  // DMMA fragment coordinates
 
-    // load lower triangle; strict upper = 0 (identity's off-diagonal); padding = identity
+    // load lower triangle; strict upper = 0 (the identity's off-diagonal); padding = identity
     for (int r = warp; r < NB; r += POTF2_THREADS / 32) {
         for (int c = lane; c < NB; c += 32) {
             double v = 0.0;
@@ -42,48 +58,105 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
             T[r * PT + c] = v;
         }
     }
+    if (tid == 0) s_fail = 0;
     __syncthreads();
 
-    int fail = 0;
-    for (int k = 0; k < NB; ++k) {
-        const double akk = T[k * PT + k];
-        if (!(akk > 0.0) && fail == 0) fail = j0 + k + 1;          // dpotf2: ajj <= 0 or NaN
-        const double d = sqrt(akk);
-        const double rinv = 1.0 / d;
-        __syncthreads();                                            // everyone has read akk
-        // scale column k: L part below the diagonal (divide), X part above it (x / d)
-        if (tid < NB) {
-            const int t = tid;
-            if (t > k)      T[t * PT + k] = T[t * PT + k] / d;
-            else if (t < k) T[t * PT + k] = T[t * PT + k] * rinv;
-            else          { T[k * PT + k] = d; dinv[k] = rinv; }
+    for (int kb = 0; kb < NB / PB; ++kb) {
+        const int k0 = kb * PB;
+        // ---------------------------------------------------------------- 32x32 diagonal sub-block, one warp
+        if (warp == 0) {
+            double a[PB], x[PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                a[c] = (c <= lane) ? T[(k0 + lane) * PT + k0 + c] : 0.0;
+                x[c] = (c == lane) ? 1.0 : 0.0;
+            }
+            int fail = 0;
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0) && fail == 0) fail = j0 + k0 + c + 1;          // dpotf2: ajj <= 0 or NaN
+                const double rinv = rsqrt(piv);
+                const double d = piv * rinv;
+                a[c] = (lane == c) ? d : a[c] * rinv;                          // column c of L
+                x[c] = x[c] * rinv;                                            // column c of X = L^-T (rows <= c)
+#pragma unroll
+                for (int j = c + 1; j < PB; ++j) {
+                    const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+                    a[j] = fma(-a[c], ljc, a[j]);
+                    x[j] = fma(-x[c], ljc, x[j]);
+                }
+            }
+            // write back: L (lower incl. diagonal) and X (strict upper) into T; clean inverse Lc[c][k] = X[k][c]
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                T[(k0 + lane) * PT + k0 + c] = (c <= lane) ? a[c] : x[c];
+                Lc[c * PC + lane] = (lane <= c) ? x[c] : 0.0;                   // row c of L_d^-1, entry k = lane
+            }
+            double xd = 0.0;
+#pragma unroll
+            for (int c = 0; c < PB; ++c) xd = (c == lane) ? x[c] : xd;           // x[lane] without dynamic indexing
+            dinv[k0 + lane] = xd;
+            if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;
         }
         __syncthreads();
-        // trailing update of columns j > k:  T[t][j] -= colk(t) * L[j][k]
-        //   rows t <= k  : X part (colk(k) = 1/d), all j > k
-        //   rows t >  k  : L part, k < j <= t
-        double ljk[4];
-        int jj[4];
+        // ---------------------------------------------------------------- sub-panel: rows above (X) and below (L)
+        //   T[r][k0 + c] = sum_k T[r][k0 + k] * Lc[c][k]        (in place; a warp owns whole rows)
+        {
+            const int nblk_above = k0 / 8, nblk_below = (NB - k0 - PB) / 8;
+            for (int u = warp; u < nblk_above + nblk_below; u += POTF2_THREADS / 32) {
+                const int r0 = (u < nblk_above) ? u * 8 : k0 + PB + (u - nblk_above) * 8;
+                double af[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            jj[q] = k + 1 + lane + 32 * q;
-            ljk[q] = (jj[q] < NB) ? T[jj[q] * PT + k] : 0.0;
-        }
-        for (int t = warp; t < NB; t += POTF2_THREADS / 32) {
-            const double ck = (t == k) ? rinv : T[t * PT + k];
-            const int jend = (t <= k) ? NB - 1 : t;                 // last column touched in this row
+                for (int ks = 0; ks < 8; ++ks) af[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];
+                double out[4][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (jj[q] <= jend) T[t * PT + jj[q]] -= ck * ljk[q];
+                for (int cb = 0; cb < 4; ++cb) {
+                    out[cb][0] = out[cb][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        dmma884_p(out[cb][0], out[cb][1], af[ks], Lc[(cb * 8 + fr) * PC + ks * 4 + fk]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+                    *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + cb * 8 + 2 * fk]) = make_double2(out[cb][0], out[cb][1]);
             }
         }
-        // no barrier needed here: the next iteration's first barrier orders these writes before
-        // column k+1 is scaled; akk of the next step is read after ... the writes of this step -> sync
+        __syncthreads();
+        // ---------------------------------------------------------------- trailing sub-blocks (column blocks cb > kb)
+        //   T[r][c] -= sum_k P[r][k] * T[c][k0 + k],   P = the sub-panel just computed (rows of the diagonal
+        //   sub-block itself contribute X_d = Lc^T).  Units of 8x8 outputs are dealt round-robin to the warps.
+        {
+            int u = 0;
+            for (int cbk = kb + 1; cbk < NB / PB; ++cbk) {
+                const int c0 = cbk * PB;
+                const int rows_x = k0 + PB;                   // X part: rows [0, k0+32)
+                const int nrb = rows_x / 8 + (NB - c0) / 8;   // + L part: rows [c0, 128)
+                for (int rb = 0; rb < nrb; ++rb) {
+                    const int r0 = (rb < rows_x / 8) ? rb * 8 : c0 + (rb - rows_x / 8) * 8;
+                    const bool diag_rows = (r0 >= k0) && (r0 < k0 + PB);
+                    for (int c8 = 0; c8 < 4; ++c8, ++u) {
+                        if ((u & 7) != warp) continue;
+                        double2 *cp = reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + c0 + c8 * 8 + 2 * fk]);
+                        double2 cv = *cp;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const int k = ks * 4 + fk;
+                            const double av = diag_rows ? Lc[k * PC + (r0 - k0 + fr)] : T[(r0 + fr) * PT + k0 + k];
+                            const double bv = T[(c0 + c8 * 8 + fr) * PT + k0 + k];
+                            dmma884_p(cv.x, cv.y, -av, bv);
+                        }
+                        *cp = cv;
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
 
-    if (fail != 0 && tid == 0) {
-        if (info[m] == 0) info[m] = fail;
+    if (tid == 0 && s_fail != 0) {
+        if (info[m] == 0) info[m] = s_fail;
     }
 
     // write L11 back (lower incl. diagonal); optionally zero the strict upper triangle

@@ -143,6 +143,9 @@ int gpmc_set_tuning(int key, int value);
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
  * register-resident DMMA (mma.sync m8n8k4 f64) and DFMA loops over the whole chip. */
 int gpmc_bench_fp64_peak(int which /*0 = DMMA, 1 = DFMA*/, int iters, double *tflops_out, double *ms_out);
+/* DMMA issue rate with `nacc` (1,2,4,8,16,32) independent accumulators per warp and `warps_per_sm` warps on every SM:
+ * the instruction-level parallelism the FP64 tensor pipe needs (tile shapes). */
+int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_out);
 
 /* Timing hooks: the library records CUDA-event durations of its own kernels per class
  * (0 assemble, 1 Cholesky update GEMM, 2 panel potf2, 3 panel trsm, 4 solve+reduce, 5 triangular inverse,
