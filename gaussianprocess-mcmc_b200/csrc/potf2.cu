@@ -14,6 +14,7 @@
 //     trailing sub-blocks are updated with FP64 DMMA (mma.sync.m8n8k4) on fragments read from T.
 // W = L11^-1 is written out dense so the panel TRSM below the block is a DMMA GEMM (gemm_dmma.cu).
 #include "common.cuh"
+#include "tri_solve.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
@@ -100,27 +101,44 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
             if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;
         }
         __syncthreads();
-        // ---------------------------------------------------------------- sub-panel: rows above (X) and below (L)
-        //   T[r][k0 + c] = sum_k T[r][k0 + k] * Lc[c][k]        (in place; a warp owns whole rows)
+        // ---------------------------------------------------------------- sub-panel
+        //   rows below (L):  solve  x L_d^T = a  by substitution, one row per thread (backward stable: the
+        //                    factor itself never goes through an explicit inverse)
+        //   rows above (X):  T[r][k0 + c] = sum_k T[r][k0 + k] * Lc[c][k]   -- this IS the inverse being built
         {
-            const int nblk_above = k0 / 8, nblk_below = (NB - k0 - PB) / 8;
-            for (int u = warp; u < nblk_above + nblk_below; u += POTF2_THREADS / 32) {
-                const int r0 = (u < nblk_above) ? u * 8 : k0 + PB + (u - nblk_above) * 8;
-                double af[8];
+            const int nbelow = NB - k0 - PB;
+            const int solve_warps = (nbelow + 31) / 32;               // warps 0..solve_warps-1 take one row per lane
+            if (warp < solve_warps) {
+                const int r = k0 + PB + tid;
+                if (tid < nbelow) {
+                    double xr[PB];
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) af[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];
-                double out[4][2];
+                    for (int c = 0; c < PB; ++c) xr[c] = T[r * PT + k0 + c];
+                    row_trsv32(xr, T + k0 * PT + k0, PT, dinv + k0);
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    out[cb][0] = out[cb][1] = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        dmma884_p(out[cb][0], out[cb][1], af[ks], Lc[(cb * 8 + fr) * PC + ks * 4 + fk]);
+                    for (int c = 0; c < PB; ++c) T[r * PT + k0 + c] = xr[c];
                 }
-                __syncwarp();
+            } else {
+                const int nblk_above = k0 / 8;
+                const int nw = POTF2_THREADS / 32 - solve_warps;
+                for (int u = warp - solve_warps; u < nblk_above; u += nw) {
+                    const int r0 = u * 8;
+                    double af[8];
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb)
-                    *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + cb * 8 + 2 * fk]) = make_double2(out[cb][0], out[cb][1]);
+                    for (int ks = 0; ks < 8; ++ks) af[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];
+                    double out[4][2];
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        out[cb][0] = out[cb][1] = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            dmma884_p(out[cb][0], out[cb][1], af[ks], Lc[(cb * 8 + fr) * PC + ks * 4 + fk]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + cb * 8 + 2 * fk]) = make_double2(out[cb][0], out[cb][1]);
+                }
             }
         }
         __syncthreads();

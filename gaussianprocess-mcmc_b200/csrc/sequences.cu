@@ -133,7 +133,7 @@ int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows,
 
 // ------------------------------------------------------------------ blocked Cholesky sequencing
 // Left-looking by block columns of NB: update the block column with everything to its left (DMMA GEMM),
-// factor the diagonal block (+ inverse), turn the rows below into L with one more DMMA GEMM.
+// factor the diagonal block (+ its inverse for inverse_sequence), solve the rows below by blocked substitution.
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper, cudaStream_t s)
 {
@@ -155,12 +155,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
         int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper, B, s);
         if (rc) return rc;
         if (j0 + NB < n) {
-            GemmArgs g{};
-            g.C = A; g.A = self; g.B = Operand{Wj, strideW, NB};
-            g.cr0 = j0 + NB; g.cc0 = j0; g.rows = n - j0 - NB; g.cols = NB;
-            g.ar0 = j0 + NB; g.br0 = 0; g.k0 = j0; g.bk0 = 0; g.klen = NB;
-            g.epi = EPI_SET;
-            rc = launch_gemm(g, B, KC_TRSM, s);
+            rc = launch_trsm_panel(A, n, j0, B, s);
             if (rc) return rc;
         }
     }

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <vector>
 #include <math.h>
+#include <stdlib.h>
 
 namespace gpmc {
 
@@ -82,6 +83,13 @@ static double host_diag_value(const double *h, int P)
     return sf2 + Sii;
 }
 
+static bool debug_on()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GPMC_DEBUG"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 struct AuxCtx {
     const double *x; int N, D, P, n_ell;
     SweepBuffers *w;
@@ -134,6 +142,8 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
         std::vector<int> failed, info;
         if ((rc = failed_items(c, w.info1, active, failed, info))) return rc;
         if (!failed.empty()) {
+            if (debug_on()) fprintf(stderr, "[gpmc] chol(K+S) failed for %zu of %d chains (first: chain %d, info %d): jitter ladder\n",
+                                    failed.size(), na, failed[0], info[failed[0]]);
             std::vector<double> th((size_t)w.cap * c.P), jit(w.cap, 0.0);
             GPMC_CUDA_CHECK(cudaMemcpyAsync(th.data(), w.theta, th.size() * 8, cudaMemcpyDeviceToHost, s));
             GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -183,6 +193,8 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
             std::vector<int> todo;
             for (int id : failed) if (info1[id] == 0) todo.push_back(id);
+            if (debug_on()) fprintf(stderr, "[gpmc] chol(R+1e-11 I) failed for %zu of %d chains (first: chain %d, info %d): jitter ladder on %zu\n",
+                                    failed.size(), na, failed[0], info[failed[0]], todo.size());
             int *cnt = w.count + 16;
             std::vector<double> jit(w.cap, 0.0), mean(w.cap, 0.0);
             std::vector<int> bad(w.cap, 0);
