@@ -151,22 +151,28 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
                 const int c0 = cbk * PB;
                 const int rows_x = k0 + PB;                   // X part: rows [0, k0+32)
                 const int nrb = rows_x / 8 + (NB - c0) / 8;   // + L part: rows [c0, 128)
-                for (int rb = 0; rb < nrb; ++rb) {
+                for (int rb = 0; rb < nrb; ++rb, ++u) {
+                    if ((u & 7) != warp) continue;
                     const int r0 = (rb < rows_x / 8) ? rb * 8 : c0 + (rb - rows_x / 8) * 8;
                     const bool diag_rows = (r0 >= k0) && (r0 < k0 + PB);
-                    for (int c8 = 0; c8 < 4; ++c8, ++u) {
-                        if ((u & 7) != warp) continue;
-                        double2 *cp = reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + c0 + c8 * 8 + 2 * fk]);
-                        double2 cv = *cp;
+                    double af[8];
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const int k = ks * 4 + fk;
-                            const double av = diag_rows ? Lc[k * PC + (r0 - k0 + fr)] : T[(r0 + fr) * PT + k0 + k];
-                            const double bv = T[(c0 + c8 * 8 + fr) * PT + k0 + k];
-                            dmma884_p(cv.x, cv.y, -av, bv);
-                        }
-                        *cp = cv;
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const int k = ks * 4 + fk;
+                        af[ks] = -(diag_rows ? Lc[k * PC + (r0 - k0 + fr)] : T[(r0 + fr) * PT + k0 + k]);
                     }
+                    double2 cv[4];
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8)
+                        cv[c8] = *reinterpret_cast<const double2 *>(&T[(r0 + fr) * PT + c0 + c8 * 8 + 2 * fk]);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8)
+                            dmma884_p(cv[c8].x, cv[c8].y, af[ks], T[(c0 + c8 * 8 + fr) * PT + k0 + ks * 4 + fk]);
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8)
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + c0 + c8 * 8 + 2 * fk]) = cv[c8];
                 }
             }
         }

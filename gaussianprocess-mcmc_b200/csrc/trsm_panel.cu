@@ -5,10 +5,13 @@
 // has condition ~1e11, and  A21 * inv(L11)  would lose cond(L11) * eps (measured: spurious "not positive definite"
 // pivots); substitution keeps the residual at eps * |X| |L11|.
 //
-// One CTA owns 128 rows of the panel in shared memory.  The 128 columns are processed in four sub-blocks of 32:
-//   solve : one row per thread, its 32 entries in registers, L entries broadcast from shared memory (row_trsv32)
-//   update: the not-yet-solved columns get  R[:, later] -= R[:, sb] * L[later, sb]^T  on FP64 DMMA fragments.
-// L11 is kept as its ten lower 32x32 blocks (stride 36: conflict-free fragments), the row tile with stride 132.
+// One CTA owns 128 rows of the panel.  Each warp keeps its 16 rows x 128 columns as FP64 DMMA accumulator
+// fragments in registers for the whole kernel.  The 128 columns are processed in four sub-blocks of 32:
+//   solve : the sub-block's columns go through shared memory to one-row-per-thread substitution (row_trsv32:
+//           the row in registers, L entries broadcast from shared memory), and are then final -> global
+//   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA, A fragments from shared
+//           memory, accumulators never leaving registers.
+// L11 is kept as its ten lower 32x32 blocks (stride 36: conflict-free fragments).
 #include "common.cuh"
 #include "tri_solve.cuh"
 #include "../../include/gpmc.h"
@@ -16,11 +19,10 @@
 namespace gpmc {
 
 constexpr int TP_ROWS = 128;
-constexpr int TP_T = 132;                     // row-tile stride
-constexpr int TP_B = 36;                      // L block stride
+constexpr int TP_B = 36;                      // stride of L blocks and of the staged sub-block
 constexpr int TP_THREADS = 256;
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
-constexpr int TP_SMEM = (TP_ROWS * TP_T + 10 * TP_LBLK + NB) * (int)sizeof(double);    // 165,376 B
+constexpr int TP_SMEM = (TP_ROWS * TP_B + 10 * TP_LBLK + NB) * (int)sizeof(double);    // 130,048 B
 
 __device__ __forceinline__ int lblk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
 
@@ -35,8 +37,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1)
 trsm_panel_kernel(BatchView A, int n, int j0)
 {
     extern __shared__ __align__(16) double sm[];
-    double *R = sm;                               // [128][132] rows of the panel
-    double *Lb = sm + TP_ROWS * TP_T;             // 10 lower blocks of L11
+    double *R = sm;                               // [128][36] the sub-block being solved
+    double *Lb = sm + TP_ROWS * TP_B;             // 10 lower blocks of L11
     double *dinv = Lb + 10 * TP_LBLK;             // [128]
     const int b = blockIdx.y;
     if (A.count && b >= *A.count) return;
@@ -58,58 +60,72 @@ trsm_panel_kernel(BatchView A, int n, int j0)
         const double2 v = *reinterpret_cast<const double2 *>(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2);
         *reinterpret_cast<double2 *>(&Lb[blk * TP_LBLK + r * TP_B + c2]) = v;
     }
-    // panel rows (zero beyond the matrix)
-    for (int e = tid; e < TP_ROWS * 64; e += TP_THREADS) {
-        const int r = e >> 6, c2 = (e & 63) * 2;
-        double2 v = make_double2(0.0, 0.0);
-        if (r < rows_valid) v = *reinterpret_cast<const double2 *>(Ab + (size_t)(row0 + r) * ld + j0 + c2);
-        *reinterpret_cast<double2 *>(&R[r * TP_T + c2]) = v;
+    // this warp's 16 rows as accumulator fragments: acc[rbl][cb8] = rows warp*16 + rbl*8 + fr, cols cb8*8 + 2fk, +1
+    double acc[2][16][2];
+#pragma unroll
+    for (int rbl = 0; rbl < 2; ++rbl) {
+        const int r = warp * 16 + rbl * 8 + fr;
+        const double *src = Ab + (size_t)(row0 + min(r, rows_valid - 1)) * ld + j0 + 2 * fk;
+#pragma unroll
+        for (int cb8 = 0; cb8 < 16; ++cb8) {
+            double2 v = make_double2(0.0, 0.0);
+            if (r < rows_valid) v = *reinterpret_cast<const double2 *>(src + cb8 * 8);
+            acc[rbl][cb8][0] = v.x;
+            acc[rbl][cb8][1] = v.y;
+        }
     }
     __syncthreads();
     if (tid < NB) {
         const int bi = tid >> 5, r = tid & 31;
         dinv[tid] = 1.0 / Lb[lblk_index(bi, bi) * TP_LBLK + r * TP_B + r];
     }
-    __syncthreads();
 
+#pragma unroll
     for (int sb = 0; sb < 4; ++sb) {
-        // ---- solve 32 columns: one row per thread
+        // ---- stage the sub-block's 32 columns
+#pragma unroll
+        for (int rbl = 0; rbl < 2; ++rbl)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<double2 *>(&R[(warp * 16 + rbl * 8 + fr) * TP_B + q * 8 + 2 * fk]) =
+                    make_double2(acc[rbl][sb * 4 + q][0], acc[rbl][sb * 4 + q][1]);
+        __syncthreads();
+        // ---- solve: one row per thread
         if (tid < TP_ROWS) {
             double x[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = R[tid * TP_T + sb * 32 + c];
+            for (int c = 0; c < 32; ++c) x[c] = R[tid * TP_B + c];
             row_trsv32(x, Lb + lblk_index(sb, sb) * TP_LBLK, TP_B, dinv + sb * 32);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) R[tid * TP_T + sb * 32 + c] = x[c];
+            for (int c = 0; c < 32; ++c) R[tid * TP_B + c] = x[c];
         }
         __syncthreads();
-        // ---- update the later column blocks with DMMA:  R[:, cb2] -= R[:, sb] * L[cb2, sb]^T
+        // ---- the solved columns are final: write them out (row r: 32 doubles = 256 contiguous bytes)
+        for (int e = tid; e < TP_ROWS * 16; e += TP_THREADS) {
+            const int r = e >> 4, c2 = (e & 15) * 2;
+            if (r < rows_valid)
+                *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + r) * ld + j0 + sb * 32 + c2) =
+                    *reinterpret_cast<const double2 *>(&R[r * TP_B + c2]);
+        }
+        // ---- update the later columns:  acc[:, cb8] -= X[:, sb] * L[cb8 rows, sb cols]^T
         if (sb < 3) {
-            int u = 0;
-            for (int cb2 = sb + 1; cb2 < 4; ++cb2) {
-                const double *Lq = Lb + lblk_index(cb2, sb) * TP_LBLK;
-                for (int rb = 0; rb < TP_ROWS / 8; ++rb) {
-                    for (int c8 = 0; c8 < 4; ++c8, ++u) {
-                        if ((u & 7) != warp) continue;
-                        double2 *cp = reinterpret_cast<double2 *>(&R[(rb * 8 + fr) * TP_T + cb2 * 32 + c8 * 8 + 2 * fk]);
-                        double2 cv = *cp;
+            double af[2][8];
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const double av = R[(rb * 8 + fr) * TP_T + sb * 32 + ks * 4 + fk];
-                            const double bv = Lq[(c8 * 8 + fr) * TP_B + ks * 4 + fk];
-                            dmma884_t(cv.x, cv.y, -av, bv);
-                        }
-                        *cp = cv;
-                    }
+            for (int rbl = 0; rbl < 2; ++rbl)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) af[rbl][ks] = -R[(warp * 16 + rbl * 8 + fr) * TP_B + ks * 4 + fk];
+#pragma unroll
+            for (int cb8 = (sb + 1) * 4; cb8 < 16; ++cb8) {
+                const double *Lq = Lb + lblk_index(cb8 >> 2, sb) * TP_LBLK + ((cb8 & 3) * 8 + fr) * TP_B + fk;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double bv = Lq[ks * 4];
+                    dmma884_t(acc[0][cb8][0], acc[0][cb8][1], af[0][ks], bv);
+                    dmma884_t(acc[1][cb8][0], acc[1][cb8][1], af[1][ks], bv);
                 }
             }
         }
         __syncthreads();
-    }
-    for (int e = tid; e < TP_ROWS * 64; e += TP_THREADS) {
-        const int r = e >> 6, c2 = (e & 63) * 2;
-        if (r < rows_valid)
-            *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + r) * ld + j0 + c2) = *reinterpret_cast<const double2 *>(&R[r * TP_T + c2]);
     }
 }
 
