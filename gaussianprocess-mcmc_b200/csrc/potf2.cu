@@ -14,7 +14,6 @@
 //     trailing sub-blocks are updated with FP64 DMMA (mma.sync.m8n8k4) on fragments read from T.
 // W = L11^-1 is written out dense so the panel TRSM below the block is a DMMA GEMM (gemm_dmma.cu).
 #include "common.cuh"
-#include "tri_solve.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
@@ -101,28 +100,41 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
             if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;
         }
         __syncthreads();
-        // ---------------------------------------------------------------- sub-panel
-        //   rows below (L):  solve  x L_d^T = a  by substitution, one row per thread (backward stable: the
-        //                    factor itself never goes through an explicit inverse)
+        // ---------------------------------------------------------------- sub-panel (12 row blocks of 8)
+        //   rows below (L):  solve  x L_d^T = a  by substitution IN THE FRAGMENT LAYOUT: column c of a row lives in
+        //                    one lane of the row's quad, the solved value is broadcast with a quad shuffle and each
+        //                    lane updates its own later columns (backward stable: no explicit inverse on the factor)
         //   rows above (X):  T[r][k0 + c] = sum_k T[r][k0 + k] * Lc[c][k]   -- this IS the inverse being built
         {
-            const int nbelow = NB - k0 - PB;
-            const int solve_warps = (nbelow + 31) / 32;               // warps 0..solve_warps-1 take one row per lane
-            if (warp < solve_warps) {
-                const int r = k0 + PB + tid;
-                if (tid < nbelow) {
-                    double xr[PB];
+            const int nblk_below = (NB - k0 - PB) / 8, nblk_above = k0 / 8;
+            for (int u = warp; u < nblk_below + nblk_above; u += POTF2_THREADS / 32) {
+                if (u < nblk_below) {
+                    const int r0 = k0 + PB + u * 8;
+                    double v[4][2];
 #pragma unroll
-                    for (int c = 0; c < PB; ++c) xr[c] = T[r * PT + k0 + c];
-                    row_trsv32(xr, T + k0 * PT + k0, PT, dinv + k0);
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]);
+                        v[q][0] = t2.x; v[q][1] = t2.y;
+                    }
 #pragma unroll
-                    for (int c = 0; c < PB; ++c) T[r * PT + k0 + c] = xr[c];
-                }
-            } else {
-                const int nblk_above = k0 / 8;
-                const int nw = POTF2_THREADS / 32 - solve_warps;
-                for (int u = warp - solve_warps; u < nblk_above; u += nw) {
-                    const int r0 = u * 8;
+                    for (int c = 0; c < PB; ++c) {
+                        const int CB = c >> 3, OW = (c & 7) >> 1, S = c & 1;
+                        const double xs = __shfl_sync(0xffffffffu, v[CB][S] * dinv[k0 + c], (lane & ~3) | OW);
+                        if (fk == OW) v[CB][S] = xs;
+#pragma unroll
+                        for (int CB2 = CB; CB2 < 4; ++CB2) {
+#pragma unroll
+                            for (int S2 = 0; S2 < 2; ++S2) {
+                                const int j = CB2 * 8 + 2 * fk + S2;
+                                if (CB2 > CB || j > c) v[CB2][S2] = fma(-xs, T[(k0 + j) * PT + k0 + c], v[CB2][S2]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]) = make_double2(v[q][0], v[q][1]);
+                } else {
+                    const int r0 = (u - nblk_below) * 8;
                     double af[8];
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) af[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];

@@ -6,14 +6,15 @@
 // pivots); substitution keeps the residual at eps * |X| |L11|.
 //
 // One CTA owns 128 rows of the panel.  Each warp keeps its 16 rows x 128 columns as FP64 DMMA accumulator
-// fragments in registers for the whole kernel.  The 128 columns are processed in four sub-blocks of 32:
-//   solve : the sub-block's columns go through shared memory to one-row-per-thread substitution (row_trsv32:
-//           the row in registers, L entries broadcast from shared memory), and are then final -> global
-//   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA, A fragments from shared
-//           memory, accumulators never leaving registers.
+// fragments in registers for the whole kernel and, after the initial load of L11, never meets a block barrier.
+// The 128 columns are processed in four sub-blocks of 32:
+//   solve : substitution in the fragment layout itself -- column c of a row lives in one lane of the row's quad;
+//           the solved value is broadcast with a quad shuffle and each lane updates its own later columns with L
+//           entries read from shared memory (no explicit inverse anywhere)
+//   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA; the solved sub-block is
+//           staged through the warp's own shared-memory rows to become A fragments (and goes out to global).
 // L11 is kept as its ten lower 32x32 blocks (stride 36: conflict-free fragments).
 #include "common.cuh"
-#include "tri_solve.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
@@ -79,33 +80,48 @@ trsm_panel_kernel(BatchView A, int n, int j0)
         const int bi = tid >> 5, r = tid & 31;
         dinv[tid] = 1.0 / Lb[lblk_index(bi, bi) * TP_LBLK + r * TP_B + r];
     }
-
+    __syncthreads();
+    // From here on every warp works on its own 16 rows only (L and dinv are read-only): no block barriers.
+    double *Rw = R + warp * 16 * TP_B;            // this warp's staging rows
 #pragma unroll
     for (int sb = 0; sb < 4; ++sb) {
-        // ---- stage the sub-block's 32 columns
+        const double *Ld = Lb + lblk_index(sb, sb) * TP_LBLK;
+        // ---- solve the sub-block's 32 columns in fragment layout.  Column c lives in lane fk == (c%8)/2 of each
+        //      row's quad; the solved value is broadcast inside the quad and every lane updates its own later columns.
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int CB = c >> 3, OW = (c & 7) >> 1, S = c & 1;
+            const double dv = dinv[sb * 32 + c];
+            const int src = (lane & ~3) | OW;
+            const double x0 = __shfl_sync(0xffffffffu, acc[0][sb * 4 + CB][S] * dv, src);
+            const double x1 = __shfl_sync(0xffffffffu, acc[1][sb * 4 + CB][S] * dv, src);
+            if (fk == OW) { acc[0][sb * 4 + CB][S] = x0; acc[1][sb * 4 + CB][S] = x1; }
+#pragma unroll
+            for (int CB2 = CB; CB2 < 4; ++CB2) {
+#pragma unroll
+                for (int S2 = 0; S2 < 2; ++S2) {
+                    const int j = CB2 * 8 + 2 * fk + S2;              // this lane's column
+                    if (CB2 > CB || j > c) {
+                        const double lv = Ld[j * TP_B + c];
+                        acc[0][sb * 4 + CB2][S2] = fma(-x0, lv, acc[0][sb * 4 + CB2][S2]);
+                        acc[1][sb * 4 + CB2][S2] = fma(-x1, lv, acc[1][sb * 4 + CB2][S2]);
+                    }
+                }
+            }
+        }
+        // ---- stage the solved columns (this warp's rows): final values -> global, and A fragments for the update
 #pragma unroll
         for (int rbl = 0; rbl < 2; ++rbl)
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<double2 *>(&R[(warp * 16 + rbl * 8 + fr) * TP_B + q * 8 + 2 * fk]) =
+                *reinterpret_cast<double2 *>(&Rw[(rbl * 8 + fr) * TP_B + q * 8 + 2 * fk]) =
                     make_double2(acc[rbl][sb * 4 + q][0], acc[rbl][sb * 4 + q][1]);
-        __syncthreads();
-        // ---- solve: one row per thread
-        if (tid < TP_ROWS) {
-            double x[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = R[tid * TP_B + c];
-            row_trsv32(x, Lb + lblk_index(sb, sb) * TP_LBLK, TP_B, dinv + sb * 32);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) R[tid * TP_B + c] = x[c];
-        }
-        __syncthreads();
-        // ---- the solved columns are final: write them out (row r: 32 doubles = 256 contiguous bytes)
-        for (int e = tid; e < TP_ROWS * 16; e += TP_THREADS) {
+        __syncwarp();
+        for (int e = lane; e < 16 * 16; e += 32) {
             const int r = e >> 4, c2 = (e & 15) * 2;
-            if (r < rows_valid)
-                *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + r) * ld + j0 + sb * 32 + c2) =
-                    *reinterpret_cast<const double2 *>(&R[r * TP_B + c2]);
+            if (warp * 16 + r < rows_valid)
+                *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + warp * 16 + r) * ld + j0 + sb * 32 + c2) =
+                    *reinterpret_cast<const double2 *>(&Rw[r * TP_B + c2]);
         }
         // ---- update the later columns:  acc[:, cb8] -= X[:, sb] * L[cb8 rows, sb cols]^T
         if (sb < 3) {
@@ -113,7 +129,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
 #pragma unroll
             for (int rbl = 0; rbl < 2; ++rbl)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) af[rbl][ks] = -R[(warp * 16 + rbl * 8 + fr) * TP_B + ks * 4 + fk];
+                for (int ks = 0; ks < 8; ++ks) af[rbl][ks] = -Rw[(rbl * 8 + fr) * TP_B + ks * 4 + fk];
 #pragma unroll
             for (int cb8 = (sb + 1) * 4; cb8 < 16; ++cb8) {
                 const double *Lq = Lb + lblk_index(cb8 >> 2, sb) * TP_LBLK + ((cb8 & 3) * 8 + fr) * TP_B + fk;
@@ -125,7 +141,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
