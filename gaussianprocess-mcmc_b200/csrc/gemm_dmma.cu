@@ -15,11 +15,9 @@
 
 namespace gpmc {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 4;
+constexpr int BM = 128, BK = 16;
 constexpr int SROW = BK + 4;                    // padded smem row (doubles)
-constexpr int OPER_ELEMS = BM * SROW;           // one operand, one stage
-constexpr int GEMM_SMEM = STAGES * 2 * OPER_ELEMS * (int)sizeof(double);   // 81,920 B
+constexpr int gemm_smem_bytes(int bn, int stages) { return stages * (BM + bn) * SROW * (int)sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
 {
@@ -36,12 +34,12 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// Stage one K=16 chunk of a 128-row operand: 128 rows x 8 16-byte pieces = 1024 pieces.
-template <int THREADS>
+// Stage one K=16 chunk of a ROWS-row operand: ROWS rows x 8 16-byte pieces.
+template <int THREADS, int ROWS>
 __device__ __forceinline__ void load_operand(double *sdst, const double *gsrc, int ld, int rows_valid, int tid)
 {
 #pragma unroll
-    for (int i = 0; i < 1024 / THREADS; ++i) {
+    for (int i = 0; i < ROWS * 8 / THREADS; ++i) {
         const int piece = tid + i * THREADS;
         const int row = piece >> 3, kc = piece & 7;
         const bool ok = row < rows_valid;
@@ -50,14 +48,17 @@ __device__ __forceinline__ void load_operand(double *sdst, const double *gsrc, i
     }
 }
 
-// WARPS_M x WARPS_N warps; each warp owns (128/WARPS_M) x (128/WARPS_N) of the tile as 8x8 DMMA fragments.
-template <int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
+// CTA tile 128 x BN; WARPS_M x WARPS_N warps, each owning (128/WARPS_M) x (BN/WARPS_N) as 8x8 DMMA fragments;
+// STAGES-deep cp.async ring; CTAS_PER_SM resident CTAs (2 lets one CTA's barrier / prologue / epilogue hide behind
+// the other's DMMA stream).
+template <int WARPS_M, int WARPS_N, int BN, int STAGES, int CTAS_PER_SM>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, CTAS_PER_SM)
 gemm_dmma_kernel(GemmArgs p)
 {
     constexpr int THREADS = WARPS_M * WARPS_N * 32;
     constexpr int FM = BM / WARPS_M / 8;        // fragments per warp along M
     constexpr int FN = BN / WARPS_N / 8;
+    constexpr int A_ELEMS = BM * SROW, STAGE_ELEMS = (BM + BN) * SROW;
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.y;
     if (p.C.count && b >= *p.C.count) return;
@@ -66,11 +67,13 @@ gemm_dmma_kernel(GemmArgs p)
     // tile decode
     int tm, tn;
     if (p.lower_only) {
+        // row tile tm has Q*(tm+1) column tiles on or below the diagonal, Q = 128 / BN
+        constexpr int Q = BM / BN;
         const int t = blockIdx.x;
-        tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
-        while (tm * (tm + 1) / 2 > t) --tm;
-        tn = t - tm * (tm + 1) / 2;
+        tm = (int)((sqrt(8.0 * (double)t / Q + 1.0) - 1.0) * 0.5);
+        while (Q * (tm + 1) * (tm + 2) / 2 <= t) ++tm;
+        while (Q * tm * (tm + 1) / 2 > t) --tm;
+        tn = t - Q * tm * (tm + 1) / 2;
     } else {
         const int tiles_n = (p.cols + BN - 1) / BN;
         tm = blockIdx.x / tiles_n;
@@ -90,14 +93,14 @@ gemm_dmma_kernel(GemmArgs p)
     const int lda = p.A.ld, ldb = p.B.ld;
     const int tid = threadIdx.x;
 
-    auto stage_a = [&](int s) { return smem + (size_t)s * 2 * OPER_ELEMS; };
-    auto stage_b = [&](int s) { return smem + (size_t)s * 2 * OPER_ELEMS + OPER_ELEMS; };
+    auto stage_a = [&](int s) { return smem + (size_t)s * STAGE_ELEMS; };
+    auto stage_b = [&](int s) { return smem + (size_t)s * STAGE_ELEMS + A_ELEMS; };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
-            load_operand<THREADS>(stage_a(s), gA + s * BK, lda, rows_valid, tid);
-            load_operand<THREADS>(stage_b(s), gB + s * BK, ldb, cols_valid, tid);
+            load_operand<THREADS, BM>(stage_a(s), gA + s * BK, lda, rows_valid, tid);
+            load_operand<THREADS, BN>(stage_b(s), gB + s * BK, ldb, cols_valid, tid);
         }
         cp_async_commit();
     }
@@ -119,8 +122,8 @@ gemm_dmma_kernel(GemmArgs p)
             const int nxt = kc + STAGES - 1;
             if (nxt < nk) {
                 const int s = nxt % STAGES;
-                load_operand<THREADS>(stage_a(s), gA + nxt * BK, lda, rows_valid, tid);
-                load_operand<THREADS>(stage_b(s), gB + nxt * BK, ldb, cols_valid, tid);
+                load_operand<THREADS, BM>(stage_a(s), gA + nxt * BK, lda, rows_valid, tid);
+                load_operand<THREADS, BN>(stage_b(s), gB + nxt * BK, ldb, cols_valid, tid);
             }
             cp_async_commit();
         }
@@ -178,8 +181,26 @@ gemm_dmma_kernel(GemmArgs p)
     }
 }
 
-static int g_gemm_cfg = 1;      // 0: 8 warps (2x4, warp tile 64x32); 1: 16 warps (4x4, warp tile 32x32)
+static int g_gemm_cfg = 1;      // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
+
+template <typename K>
+static int launch_variant(K kernel, const GemmArgs &a, int B, int bn, int threads, int smem, int kclass, cudaStream_t s, bool &attr_set)
+{
+    if (!attr_set) {
+        GPMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int tiles_m = (a.rows + BM - 1) / BM;
+    const int tiles_n = (a.cols + bn - 1) / bn;
+    const int tiles = a.lower_only ? (BM / bn) * tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+    dim3 grid(tiles, B);
+    prof_begin(kclass, s);
+    kernel<<<grid, threads, smem, s>>>(a);
+    prof_end(kclass, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
 {
@@ -189,22 +210,10 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
                   a.k0, a.bk0, a.cc0, a.A.ld, a.B.ld, a.C.ld);
         return GPMC_EALIGN;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        attr_set = true;
-    }
-    const int tiles_m = (a.rows + BM - 1) / BM;
-    const int tiles_n = (a.cols + BN - 1) / BN;
-    const int tiles = a.lower_only ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
-    dim3 grid(tiles, B);
-    prof_begin(kclass, s);
-    if (g_gemm_cfg == 0) gemm_dmma_kernel<2, 4><<<grid, 256, GEMM_SMEM, s>>>(a);
-    else gemm_dmma_kernel<4, 4><<<grid, 512, GEMM_SMEM, s>>>(a);
-    prof_end(kclass, s);
-    GPMC_LAUNCH_CHECK();
-    return 0;
+    static bool set0 = false, set1 = false, set2 = false;
+    if (g_gemm_cfg == 0) return launch_variant(gemm_dmma_kernel<2, 4, 128, 4, 1>, a, B, 128, 256, gemm_smem_bytes(128, 4), kclass, s, set0);
+    if (g_gemm_cfg == 2) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
+    return launch_variant(gemm_dmma_kernel<4, 4, 128, 4, 1>, a, B, 128, 512, gemm_smem_bytes(128, 4), kclass, s, set1);
 }
 
 }  // namespace gpmc
