@@ -181,7 +181,7 @@ gemm_dmma_kernel(GemmArgs p)
     }
 }
 
-static int g_gemm_cfg = 1;      // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM
+static int g_gemm_cfg = 2;      // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 template <typename K>
