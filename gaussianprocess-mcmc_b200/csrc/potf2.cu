@@ -49,13 +49,22 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;  // DMMA fragment coordinates
 
-    // load lower triangle; strict upper = 0 (the identity's off-diagonal); padding = identity
+    // stage the block with 16-byte cp.async pieces (all in flight at once), then fix up in shared memory:
+    // strict upper = 0 (the identity's off-diagonal), rows/cols beyond the matrix = identity
+    for (int e = tid; e < NB * (NB / 2); e += POTF2_THREADS) {
+        const int r = e >> 6, c2 = (e & 63) * 2;
+        if (r < nv && c2 <= r) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&T[r * PT + c2]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)r * ld + c2));
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
     for (int r = warp; r < NB; r += POTF2_THREADS / 32) {
         for (int c = lane; c < NB; c += 32) {
-            double v = 0.0;
-            if (r < nv && c <= r) v = Ab[(size_t)r * ld + c];
-            else if (r >= nv && c == r) v = 1.0;
-            T[r * PT + c] = v;
+            if (r >= nv) T[r * PT + c] = (c == r) ? 1.0 : 0.0;
+            else if (c > r) T[r * PT + c] = 0.0;
         }
     }
     if (tid == 0) s_fail = 0;

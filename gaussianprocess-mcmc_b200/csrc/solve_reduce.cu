@@ -77,6 +77,7 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ va, const dou
                 const int r = r0 + warp * 8 + rr + q;
                 rowp[q] = Lb + (size_t)min(r, n - 1) * ld;
             }
+#pragma unroll 4
             for (int k = 2 * lane; k < kmax; k += 64) {
                 const double2 zz = *reinterpret_cast<const double2 *>(z + k);
 #pragma unroll

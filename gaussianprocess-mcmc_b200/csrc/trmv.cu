@@ -32,6 +32,7 @@ trmv_kernel(BatchView T, int n, int upper, int mode, const double *__restrict__ 
         const int ka = (k_lo + 1) & ~1;                 // first even index >= k_lo
         const int kb = k_hi & ~1;                       // even end of the vector part
         if (k_lo < ka && k_lo < k_hi && lane == 0) acc = fma(row[k_lo], xv[k_lo], acc);
+#pragma unroll 8
         for (int k = ka + 2 * lane; k < kb; k += 64) {
             const double2 t = *reinterpret_cast<const double2 *>(row + k);
             const double2 v = *reinterpret_cast<const double2 *>(xv + k);

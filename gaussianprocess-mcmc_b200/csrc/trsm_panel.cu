@@ -5,7 +5,7 @@
 // has condition ~1e11, and  A21 * inv(L11)  would lose cond(L11) * eps (measured: spurious "not positive definite"
 // pivots); substitution keeps the residual at eps * |X| |L11|.
 //
-// One CTA owns 128 rows of the panel.  Each warp keeps its 16 rows x 128 columns as FP64 DMMA accumulator
+// One CTA owns 128 rows of the panel.  Each of its 16 warps keeps 8 rows x 128 columns as FP64 DMMA accumulator
 // fragments in registers for the whole kernel and, after the initial load of L11, never meets a block barrier.
 // The 128 columns are processed in four sub-blocks of 32:
 //   solve : substitution in the fragment layout itself -- column c of a row lives in one lane of the row's quad;
@@ -13,15 +13,16 @@
 //           entries read from shared memory (no explicit inverse anywhere)
 //   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA; the solved sub-block is
 //           staged through the warp's own shared-memory rows to become A fragments (and goes out to global).
-// L11 is kept as its ten lower 32x32 blocks (stride 36: conflict-free fragments).
+// L11 is kept as its ten lower 32x32 blocks, staged with cp.async.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
 
 constexpr int TP_ROWS = 128;
-constexpr int TP_B = 36;                      // stride of L blocks and of the staged sub-block
-constexpr int TP_THREADS = 256;
+constexpr int TP_B = 34;                      // stride of L blocks and of the staged sub-block: the substitution's
+                                              // L[j][c] reads (j = 2*fk + ..) fall in 4 distinct bank groups
+constexpr int TP_THREADS = 512;               // 16 warps x 8 rows: the kernel is latency bound, warps hide it
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
 constexpr int TP_SMEM = (TP_ROWS * TP_B + 10 * TP_LBLK + NB) * (int)sizeof(double);    // 130,048 B
 
@@ -51,30 +52,32 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
 
-    // L11 (rows/cols j0 .. j0+127), lower 32-blocks; the strict upper part of diagonal blocks is never read
-    for (int e = tid; e < 10 * 32 * 16; e += TP_THREADS) {        // 16 double2 per block row
+    // L11 (rows/cols j0 .. j0+127), lower 32-blocks, 16-byte cp.async pieces (all in flight at once);
+    // the strict upper part of diagonal blocks is never read
+    for (int e = tid; e < 10 * 32 * 16; e += TP_THREADS) {        // 16 pieces per block row
         const int blk = e / (32 * 16), rem = e - blk * 32 * 16;
         const int r = rem / 16, c2 = (rem - r * 16) * 2;
         int bi = 0;
         while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
         const int bj = blk - bi * (bi + 1) / 2;
-        const double2 v = *reinterpret_cast<const double2 *>(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2);
-        *reinterpret_cast<double2 *>(&Lb[blk * TP_LBLK + r * TP_B + c2]) = v;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&Lb[blk * TP_LBLK + r * TP_B + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2));
     }
-    // this warp's 16 rows as accumulator fragments: acc[rbl][cb8] = rows warp*16 + rbl*8 + fr, cols cb8*8 + 2fk, +1
-    double acc[2][16][2];
-#pragma unroll
-    for (int rbl = 0; rbl < 2; ++rbl) {
-        const int r = warp * 16 + rbl * 8 + fr;
+    asm volatile("cp.async.commit_group;\n" ::);
+    // this warp's 8 rows as accumulator fragments: acc[cb8] = row warp*8 + fr, cols cb8*8 + 2fk, +1
+    double acc[16][2];
+    {
+        const int r = warp * 8 + fr;
         const double *src = Ab + (size_t)(row0 + min(r, rows_valid - 1)) * ld + j0 + 2 * fk;
 #pragma unroll
         for (int cb8 = 0; cb8 < 16; ++cb8) {
             double2 v = make_double2(0.0, 0.0);
             if (r < rows_valid) v = *reinterpret_cast<const double2 *>(src + cb8 * 8);
-            acc[rbl][cb8][0] = v.x;
-            acc[rbl][cb8][1] = v.y;
+            acc[cb8][0] = v.x;
+            acc[cb8][1] = v.y;
         }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
     if (tid < NB) {
         const int bi = tid >> 5, r = tid & 31;
@@ -82,7 +85,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     }
     __syncthreads();
     // From here on every warp works on its own 16 rows only (L and dinv are read-only): no block barriers.
-    double *Rw = R + warp * 16 * TP_B;            // this warp's staging rows
+    double *Rw = R + warp * 8 * TP_B;             // this warp's staging rows
 #pragma unroll
     for (int sb = 0; sb < 4; ++sb) {
         const double *Ld = Lb + lblk_index(sb, sb) * TP_LBLK;
@@ -91,54 +94,38 @@ trsm_panel_kernel(BatchView A, int n, int j0)
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             const int CB = c >> 3, OW = (c & 7) >> 1, S = c & 1;
-            const double dv = dinv[sb * 32 + c];
-            const int src = (lane & ~3) | OW;
-            const double x0 = __shfl_sync(0xffffffffu, acc[0][sb * 4 + CB][S] * dv, src);
-            const double x1 = __shfl_sync(0xffffffffu, acc[1][sb * 4 + CB][S] * dv, src);
-            if (fk == OW) { acc[0][sb * 4 + CB][S] = x0; acc[1][sb * 4 + CB][S] = x1; }
+            const double xs = __shfl_sync(0xffffffffu, acc[sb * 4 + CB][S] * dinv[sb * 32 + c], (lane & ~3) | OW);
+            if (fk == OW) acc[sb * 4 + CB][S] = xs;
 #pragma unroll
             for (int CB2 = CB; CB2 < 4; ++CB2) {
 #pragma unroll
                 for (int S2 = 0; S2 < 2; ++S2) {
                     const int j = CB2 * 8 + 2 * fk + S2;              // this lane's column
-                    if (CB2 > CB || j > c) {
-                        const double lv = Ld[j * TP_B + c];
-                        acc[0][sb * 4 + CB2][S2] = fma(-x0, lv, acc[0][sb * 4 + CB2][S2]);
-                        acc[1][sb * 4 + CB2][S2] = fma(-x1, lv, acc[1][sb * 4 + CB2][S2]);
-                    }
+                    if (CB2 > CB || j > c) acc[sb * 4 + CB2][S2] = fma(-xs, Ld[j * TP_B + c], acc[sb * 4 + CB2][S2]);
                 }
             }
         }
         // ---- stage the solved columns (this warp's rows): final values -> global, and A fragments for the update
 #pragma unroll
-        for (int rbl = 0; rbl < 2; ++rbl)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<double2 *>(&Rw[(rbl * 8 + fr) * TP_B + q * 8 + 2 * fk]) =
-                    make_double2(acc[rbl][sb * 4 + q][0], acc[rbl][sb * 4 + q][1]);
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
         __syncwarp();
-        for (int e = lane; e < 16 * 16; e += 32) {
+        for (int e = lane; e < 8 * 16; e += 32) {
             const int r = e >> 4, c2 = (e & 15) * 2;
-            if (warp * 16 + r < rows_valid)
-                *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + warp * 16 + r) * ld + j0 + sb * 32 + c2) =
+            if (warp * 8 + r < rows_valid)
+                *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + warp * 8 + r) * ld + j0 + sb * 32 + c2) =
                     *reinterpret_cast<const double2 *>(&Rw[r * TP_B + c2]);
         }
         // ---- update the later columns:  acc[:, cb8] -= X[:, sb] * L[cb8 rows, sb cols]^T
         if (sb < 3) {
-            double af[2][8];
+            double af[8];
 #pragma unroll
-            for (int rbl = 0; rbl < 2; ++rbl)
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) af[rbl][ks] = -Rw[(rbl * 8 + fr) * TP_B + ks * 4 + fk];
+            for (int ks = 0; ks < 8; ++ks) af[ks] = -Rw[fr * TP_B + ks * 4 + fk];
 #pragma unroll
             for (int cb8 = (sb + 1) * 4; cb8 < 16; ++cb8) {
                 const double *Lq = Lb + lblk_index(cb8 >> 2, sb) * TP_LBLK + ((cb8 & 3) * 8 + fr) * TP_B + fk;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const double bv = Lq[ks * 4];
-                    dmma884_t(acc[0][cb8][0], acc[0][cb8][1], af[0][ks], bv);
-                    dmma884_t(acc[1][cb8][0], acc[1][cb8][1], af[1][ks], bv);
-                }
+                for (int ks = 0; ks < 8; ++ks) dmma884_t(acc[cb8][0], acc[cb8][1], af[ks], Lq[ks * 4]);
             }
         }
         __syncwarp();
