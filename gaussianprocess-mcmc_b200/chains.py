@@ -27,7 +27,8 @@ class ChainEnsemble(object):
     with ``sharded_input=True``); ``sweep(it)`` advances every local chain by one transition and returns the gathered
     ``(Hyp[B,P], loglik[B], ntrips[B])`` as numpy arrays on every rank."""
 
-    def __init__(self, x, y, F0, Hyp0, scale, seed=0, max_trips=64, sweeper=None, gather_f=False, sharded_input=False):
+    def __init__(self, x, y, F0, Hyp0, scale, seed=0, max_trips=64, sweeper=None, gather_f=False, sharded_input=False,
+                 distributed=True):
         self.x = np.asarray(x, dtype=np.float64)
         if self.x.ndim == 1:
             self.x = self.x.reshape(-1, 1)
@@ -39,7 +40,7 @@ class ChainEnsemble(object):
         self.rank, self.world = 0, 1
         try:
             import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
+            if distributed and dist.is_available() and dist.is_initialized():
                 self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
         except ImportError:
             pass
