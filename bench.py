@@ -182,6 +182,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (the image default); keep stdout for the JSON line
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     if args.gemm_cfg is not None:
@@ -316,7 +319,8 @@ def run_b200(args):
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(sum(v[1] for v in prof.values())),
         'roofline': roofline, 'cpu_baseline': cpu,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
