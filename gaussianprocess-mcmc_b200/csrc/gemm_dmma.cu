@@ -11,7 +11,9 @@
 // shared rows are padded to 20 doubles so the 8-byte fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct
 // bank pairs (ncu: 0 shared bank conflicts).  Rows beyond the matrix are zero-filled by cp.async's src-size operand.
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "../../include/gpmc.h"
+#include <stdlib.h>
 
 namespace gpmc {
 
@@ -26,13 +28,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 
 // Stage one K=16 chunk of a ROWS-row operand: ROWS rows x 8 16-byte pieces.
 template <int THREADS, int ROWS>
@@ -64,21 +59,8 @@ gemm_dmma_kernel(GemmArgs p)
     if (p.C.count && b >= *p.C.count) return;
     const int m = batch_item(p.C, b);
 
-    // tile decode
     int tm, tn;
-    if (p.lower_only) {
-        // row tile tm has Q*(tm+1) column tiles on or below the diagonal, Q = 128 / BN
-        constexpr int Q = BM / BN;
-        const int t = blockIdx.x;
-        tm = (int)((sqrt(8.0 * (double)t / Q + 1.0) - 1.0) * 0.5);
-        while (Q * (tm + 1) * (tm + 2) / 2 <= t) ++tm;
-        while (Q * tm * (tm + 1) / 2 > t) --tm;
-        tn = t - Q * tm * (tm + 1) / 2;
-    } else {
-        const int tiles_n = (p.cols + BN - 1) / BN;
-        tm = blockIdx.x / tiles_n;
-        tn = blockIdx.x - tm * tiles_n;
-    }
+    gemm_tile_decode<BM, BN>(p, blockIdx.x, tm, tn);
     const int rows_valid = min(BM, p.rows - tm * BM);
     const int cols_valid = min(BN, p.cols - tn * BN);
 
@@ -144,44 +126,14 @@ gemm_dmma_kernel(GemmArgs p)
     }
     cp_async_wait<0>();
 
-    // epilogue: each thread owns, per fragment, row = lane/4 and two adjacent columns 2*(lane%4)
-    double *Cb = p.C.base + (size_t)m * p.C.stride;
-    const int ldc = p.C.ld;
-    const double *sv = (p.epi == EPI_R) ? p.svec + (size_t)m * p.stride_s : nullptr;
-#pragma unroll
-    for (int i = 0; i < FM; ++i) {
-        const int rl = wm * FM * 8 + i * 8 + frow;
-        if (rl >= rows_valid) continue;
-        const int gr = p.cr0 + tm * BM + rl;
-        double *crow = Cb + (size_t)gr * ldc + p.cc0 + tn * BN;
-        const double s_r = sv ? sv[gr] : 0.0;
-#pragma unroll
-        for (int j = 0; j < FN; ++j) {
-            const int cl = wn * FN * 8 + j * 8 + fk * 2;
-            if (cl >= cols_valid) continue;
-            const bool two = (cl + 1 < cols_valid);
-            double v0 = acc[i][j][0], v1 = acc[i][j][1];
-            if (p.epi == EPI_SUB) {
-                if (two) { const double2 c = *reinterpret_cast<const double2 *>(crow + cl); v0 = c.x - v0; v1 = c.y - v1; }
-                else v0 = crow[cl] - v0;
-            } else if (p.epi == EPI_NEGSET) {
-                v0 = -v0; v1 = -v1;
-            } else if (p.epi == EPI_R) {
-                // R = S - S P S  (+ 1e-11 on the diagonal, sliceSample.py:205)
-                const int gc = p.cc0 + tn * BN + cl;
-                const double s_c0 = sv[gc], s_c1 = two ? sv[gc + 1] : 0.0;
-                v0 = -(s_r * v0 * s_c0);
-                v1 = -(s_r * v1 * s_c1);
-                if (gr == gc) v0 = (s_r + v0) + 1e-11;
-                if (gr == gc + 1) v1 = (s_r + v1) + 1e-11;
-            }
-            if (two) *reinterpret_cast<double2 *>(crow + cl) = make_double2(v0, v1);
-            else crow[cl] = v0;
-        }
-    }
+    gemm_epilogue<FM, FN, BM, BN>(p, m, tm, tn, wm, wn, frow, fk, rows_valid, cols_valid, acc);
 }
 
-static int g_gemm_cfg = 2;      // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM
+bool gemm_tma_supported(const GemmArgs &a);
+int launch_gemm_tma(const GemmArgs &a, int B, int kclass, cudaStream_t s);
+
+// 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged
+static int g_gemm_cfg = 2;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 template <typename K>
@@ -210,9 +162,15 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
                   a.k0, a.bk0, a.cc0, a.A.ld, a.B.ld, a.C.ld);
         return GPMC_EALIGN;
     }
-    static bool set0 = false, set1 = false, set2 = false;
+    static bool set0 = false, set1 = false, set2 = false, env_read = false;
+    if (!env_read) {            // GPMC_GEMM_CFG=0..3 selects the tile-kernel variant (experiments / A-B tests)
+        const char *e = getenv("GPMC_GEMM_CFG");
+        if (e && e[0] >= '0' && e[0] <= '3') g_gemm_cfg = e[0] - '0';
+        env_read = true;
+    }
+    if (g_gemm_cfg == 3 && gemm_tma_supported(a)) return launch_gemm_tma(a, B, kclass, s);
     if (g_gemm_cfg == 0) return launch_variant(gemm_dmma_kernel<2, 4, 128, 4, 1>, a, B, 128, 256, gemm_smem_bytes(128, 4), kclass, s, set0);
-    if (g_gemm_cfg == 2) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
+    if (g_gemm_cfg == 2 || g_gemm_cfg == 3) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
     return launch_variant(gemm_dmma_kernel<4, 4, 128, 4, 1>, a, B, 128, 512, gemm_smem_bytes(128, 4), kclass, s, set1);
 }
 
