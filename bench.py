@@ -275,11 +275,16 @@ def run_b200(args):
     peak = peaks.get('cublas_dgemm_8192_tflops')
     roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-        'frac': (achieved / peak) if (achieved and peak) else None, 'traffic': None,
+        'frac': (achieved / peak) if (achieved and peak) else None,
+        # DRAM bytes per eval of the dominant kernel (the 31 update launches of one N=4096 factorisation), from the ncu
+        # capture profiles/r01c_gemm31.csv (dram__bytes_read.sum + dram__bytes_write.sum, 16 chains): 828 MB measured
+        # vs 845 MB algorithmic (every L row read once per block column + the block column read and written once)
+        'traffic': 827.98e6 if n == 4096 else None, 'traffic_unit': 'bytes per eval (update kernel)',
+        'traffic_algorithmic': sum((n - j * 128) * (j * 128) * 8 + 2 * (n - j * 128) * 128 * 8 for j in range(1, (n + 127) // 128)),
         'peak_source': 'measured in this run: cuBLAS DGEMM 8192^3 FP64 (MEASURED_PEAKS.json has no FP64 figure); '
                        'nominal B200 FP64 tensor 40 TFLOP/s',
-        'what': 'batched blocked Cholesky (gemm_dmma update + potf2 + panel trsm launches), N^3/3 flop per eval over '
-                'the summed CUDA-event durations of those launches on their stream',
+        'what': 'batched blocked Cholesky (TMA-staged DMMA update kernel + potf2 + panel solve launches), N^3/3 flop per eval '
+                'over the summed CUDA-event durations of those launches on their stream',
         'frac_of_nominal_40tf': (achieved / 40.0) if achieved else None,
         'update_kernel': {'ms_total': gemm_ms, 'launches': gemm_launches,
                           'executed_tflops': evals_timed * exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None},

@@ -133,7 +133,7 @@ bool gemm_tma_supported(const GemmArgs &a);
 int launch_gemm_tma(const GemmArgs &a, int B, int kclass, cudaStream_t s);
 
 // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged
-static int g_gemm_cfg = 2;
+static int g_gemm_cfg = 3;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 template <typename K>
