@@ -88,6 +88,15 @@ __global__ void __launch_bounds__(256) write_diag_block_T_kernel(BatchView A, in
     }
 }
 
+// A[i][i] += v[i] (per-item vector); used to form K + S for a caller-supplied K
+__global__ void add_diag_vec_kernel(BatchView A, int n, const double *v, int ldv)
+{
+    const int b = blockIdx.y;
+    const int m = batch_item(A, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A.base[(size_t)m * A.stride + (size_t)i * A.ld + i] += v[(size_t)m * ldv + i];
+}
+
 __global__ void copy_rows_kernel(double *dst, int ldd, const double *src, int lds, int n)
 {
     const int r = blockIdx.y;
@@ -120,6 +129,22 @@ int diag_stats(BatchView A, int n, double *mean_out, int *nonpos_out, int B, cud
 {
     if (B <= 0) return 0;
     diag_stats_kernel<<<B, 256, 0, s>>>(A, n, mean_out, nonpos_out);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int add_diag_vec(BatchView A, int n, const double *v, int ldv, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    add_diag_vec_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(A, n, v, ldv);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+int zero_upper(BatchView A, int n, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    dim3 blk(32, 8);
+    dim3 grid((n + 31) / 32, (n + 7) / 8, B);
+    zero_upper_kernel<<<grid, blk, 0, s>>>(A, n);
     GPMC_LAUNCH_CHECK();
     return 0;
 }

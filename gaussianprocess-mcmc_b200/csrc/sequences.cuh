@@ -22,6 +22,8 @@ int fill_int(int *p, int v, int n, cudaStream_t s);
 int fill_int_mapped(int *p, int v, const int *map, const int *count, int nmax, cudaStream_t s);
 int add_diag(BatchView A, int n, const double *jitter, int B, cudaStream_t s);
 int diag_stats(BatchView A, int n, double *mean_out, int *nonpos_out, int B, cudaStream_t s);
+int add_diag_vec(BatchView A, int n, const double *v, int ldv, int B, cudaStream_t s);
+int zero_upper(BatchView A, int n, int B, cudaStream_t s);
 int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows, cudaStream_t s);
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

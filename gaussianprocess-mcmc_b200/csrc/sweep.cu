@@ -237,6 +237,63 @@ using namespace gpmc;
 
 extern "C" {
 
+// ---------------------------------------------------------------------------------------------------------
+// aux_var_model(f, K, sn, g) for ONE caller-supplied covariance matrix (sliceSample.py:165-207): the caller passes K
+// and the diagonal of S (sliceSample.py:184-190, O(N) host arithmetic) and g; returns L = chol(K+S) (:196),
+// m = R S^-1 g (:204) and C = chol(R + 1e-11 I) (:205), all N x ld row-major lower triangular with zeroed upper part.
+size_t gpmc_aux_workspace_bytes(int N)
+{
+    if (N <= 0) return 0;
+    const size_t nt = (N + NB - 1) / NB;
+    return align_up((size_t)N * ld_for(N) * 8, 256) + align_up(nt * NB * NB * 8, 256) + align_up((size_t)NB * NB * 8, 256)
+           + 2 * align_up((size_t)ld_for(N) * 8, 256) + 1024;
+}
+
+int gpmc_aux_var_model(const double *K_dev, int N, int ld, const double *S_dev, const double *g_dev, double *L_dev,
+                       double *m_dev, double *C_dev, int *info_dev /*[2]*/, void *ws_dev, size_t ws_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N <= 0 || ld < N || (ld & 15)) { set_error("aux_var_model: need ld %% 16 == 0 and ld >= N (N=%d ld=%d)", N, ld); return GPMC_EALIGN; }
+    if (!ws_dev || ws_bytes < gpmc_aux_workspace_bytes(N)) { set_error("aux_var_model: workspace too small"); return GPMC_ENOMEM; }
+    const int nt = (N + NB - 1) / NB;
+    char *p = (char *)ws_dev;
+    double *U = (double *)p; p += align_up((size_t)N * ld * 8, 256);
+    double *Wsave = (double *)p; p += align_up((size_t)nt * NB * NB * 8, 256);
+    double *Wtmp = (double *)p; p += align_up((size_t)NB * NB * 8, 256);
+    double *z = (double *)p; p += align_up((size_t)ld * 8, 256);
+    const long long mat = (long long)N * ld;
+    int rc;
+    if ((rc = fill_int(info_dev, 0, 2, s))) return rc;
+    // K + S -> L (in the caller's L buffer), keeping the block inverses
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(L_dev, K_dev, (size_t)mat * 8, cudaMemcpyDeviceToDevice, s));
+    BatchView Lv{L_dev, mat, ld, nullptr, nullptr};
+    if ((rc = add_diag_vec(Lv, N, S_dev, ld, 1, s))) return rc;
+    if ((rc = potrf_sequence(Lv, N, 1, info_dev, Wsave, (long long)nt * NB * NB, NB * NB, 0, s))) return rc;
+    if ((rc = launch_solve_reduce(Lv, N, g_dev, nullptr, ld, z, nullptr, info_dev, 1, s))) return rc;
+    // U = L^-T on a copy (L itself is an output)
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(U, L_dev, (size_t)mat * 8, cudaMemcpyDeviceToDevice, s));
+    BatchView Uv{U, mat, ld, nullptr, nullptr};
+    if ((rc = inverse_sequence(Uv, N, 1, Wsave, (long long)nt * NB * NB, s))) return rc;
+    if ((rc = launch_trmv(Uv, N, 1, 1, z, g_dev, S_dev, ld, m_dev, 1, s))) return rc;
+    BatchView Cv{C_dev, mat, ld, nullptr, nullptr};
+    if ((rc = r_sequence(Cv, Uv, N, 1, S_dev, ld, s))) return rc;
+    if ((rc = potrf_sequence(Cv, N, 1, info_dev + 1, Wtmp, NB * NB, 0, 0, s))) return rc;
+    if ((rc = zero_upper(Lv, N, 1, s))) return rc;
+    if ((rc = zero_upper(Cv, N, 1, s))) return rc;
+    return 0;
+}
+
+// Forward substitution  L x = b  for B right-hand sides; strideL = 0 shares one L between all of them.
+// (the solve inside tools.solve_chol, sliceSample.py:258, and inside inf_mcmc, :269)
+int gpmc_trsv_lower_batched(const double *L_dev, int N, int ld, long long strideL, const double *rhs_dev, int ldv, int B,
+                            double *out_dev, double *quad_dev, void *stream)
+{
+    if (N <= 0 || B < 0 || ld < N || (ld & 1) || (ldv & 1) || ldv < N) { set_error("trsv: bad shape N=%d ld=%d ldv=%d B=%d", N, ld, ldv, B); return GPMC_EINVAL; }
+    BatchView Lv{const_cast<double *>(L_dev), strideL, ld, nullptr, nullptr};
+    // quad_dev (optional) receives -(0.5 x.x + sum log L_ii + 0.5 N log 2pi), i.e. log N(b; 0, L L^T)
+    return launch_solve_reduce(Lv, N, rhs_dev, nullptr, ldv, out_dev, quad_dev, nullptr, B, (cudaStream_t)stream);
+}
+
 size_t gpmc_sds_workspace_bytes(int N, int P, int chains_per_wave)
 {
     if (N <= 0 || P < 3 || chains_per_wave <= 0) return 0;

@@ -241,6 +241,96 @@ def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max
     return ntrips, loglik, status
 
 
+def _pad_matrix(torch, A, ld):
+    """Copy a host/device [N, N] matrix into a zero-padded CUDA [N, ld] buffer."""
+    A = _f64_cuda(torch, A, 'A')
+    N = A.shape[0]
+    out = torch.zeros((N, ld), dtype=torch.float64, device='cuda')
+    out[:, :A.shape[1]] = A
+    return out
+
+
+def aux_var_model_device(K, Sdiag, g):
+    """L = chol(K+S), m = R S^-1 g, C = chol(R + 1e-11 I) for one caller-supplied K (``sliceSample.py:196-205``).
+
+    Returns device tensors ``(L[N,N], m[N], C[N,N], info[2])``; no jitter retry (see kcMCMC.sliceSample.aux_var_model)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    N = int(K.shape[0])
+    ld = (N + 15) // 16 * 16
+    Kp = _pad_matrix(torch, K, ld)
+    Sv = torch.zeros((ld,), dtype=torch.float64, device='cuda')
+    Sv[:N] = _f64_cuda(torch, Sdiag, 'S').reshape(-1)
+    gv = torch.zeros((ld,), dtype=torch.float64, device='cuda')
+    gv[:N] = _f64_cuda(torch, g, 'g').reshape(-1)
+    L = torch.zeros((N, ld), dtype=torch.float64, device='cuda')
+    C = torch.zeros((N, ld), dtype=torch.float64, device='cuda')
+    m = torch.zeros((ld,), dtype=torch.float64, device='cuda')
+    info = torch.zeros((2,), dtype=torch.int32, device='cuda')
+    ws = _default_ws.get(torch, lib.gpmc_aux_workspace_bytes(N))
+    rc = lib.gpmc_aux_var_model(Kp.data_ptr(), N, ld, Sv.data_ptr(), gv.data_ptr(), L.data_ptr(), m.data_ptr(), C.data_ptr(),
+                                info.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_aux_var_model')
+    return L[:, :N], m[:N], C[:, :N], info
+
+
+def trsv_lower(L, rhs, want_lognormal=False):
+    """Solve ``L x = b`` for every row ``b`` of ``rhs[B, N]`` with ONE lower-triangular ``L[N, N]`` (device tensors out)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    N = int(L.shape[0])
+    ld = (N + 15) // 16 * 16
+    Lp = _pad_matrix(torch, L, ld)
+    rhs = _f64_cuda(torch, rhs, 'rhs')
+    if rhs.dim() == 1:
+        rhs = rhs.reshape(1, -1)
+    B = rhs.shape[0]
+    R = torch.zeros((B, ld), dtype=torch.float64, device='cuda')
+    R[:, :N] = rhs
+    out = torch.empty((B, ld), dtype=torch.float64, device='cuda')
+    quad = torch.empty((B,), dtype=torch.float64, device='cuda') if want_lognormal else None
+    rc = lib.gpmc_trsv_lower_batched(Lp.data_ptr(), N, ld, 0, R.data_ptr(), ld, B, out.data_ptr(),
+                                     None if quad is None else quad.data_ptr(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_trsv_lower_batched')
+    return (out[:, :N], quad) if want_lognormal else out[:, :N]
+
+
+def cov_cross(x, z, hyp):
+    """``covK.RBF(...).getCovMatrix(x=x, z=z, mode='cross')`` -> device tensor ``[N, M]`` (``sliceSample.py:263``)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x'); z = _f64_cuda(torch, z, 'z')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    if z.dim() == 1:
+        z = z.reshape(-1, 1)
+    hyp = _f64_cuda(torch, hyp, 'hyp').reshape(-1)
+    N, D = x.shape
+    M = z.shape[0]
+    out = torch.empty((N, M), dtype=torch.float64, device='cuda')
+    rc = lib.gpmc_cov_cross(x.data_ptr(), N, z.data_ptr(), M, D, hyp.data_ptr(), hyp.numel(), kind_of(D, hyp.numel()),
+                            out.data_ptr(), M, _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_cov_cross')
+    return out
+
+
+def tg2_loglik(y, mu, sn, lower, upper, my=0.0):
+    """``likK.TruncatedGauss2(upper, lower, ...).evaluate(y=y - my, mu=mu_b)`` for every row of ``mu[B, N]``."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    y = _f64_cuda(torch, y, 'y').reshape(-1)
+    mu = _f64_cuda(torch, mu, 'mu')
+    if mu.dim() == 1:
+        mu = mu.reshape(1, -1)
+    B, N = mu.shape
+    sn = _f64_cuda(torch, np.broadcast_to(np.asarray(sn, dtype=np.float64), (B,)).copy(), 'sn')
+    out = torch.empty((B,), dtype=torch.float64, device='cuda')
+    rc = lib.gpmc_tg2_loglik(y.data_ptr(), float(my), mu.data_ptr(), N, N, B, sn.data_ptr(), float(lower), float(upper),
+                             out.data_ptr(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_tg2_loglik')
+    return out
+
+
 def set_tuning(key, value):
     _lib.check(_lib.load().gpmc_set_tuning(int(key), int(value)), 'gpmc_set_tuning')
 

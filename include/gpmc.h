@@ -137,6 +137,39 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
                    int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
                    void *ws_dev, size_t ws_bytes, void *stream);
 
+/*
+ * aux_var_model(f, K, sn, g) for one caller-supplied K (sliceSample.py:165-207).  K_dev[N][ld] (ld % 16 == 0, pad
+ * columns zero), S_dev[ld] = diag of S (sliceSample.py:184-190; entries beyond N zero), g_dev[ld].  Outputs
+ * L_dev = chol(K+S) (:196), m_dev[ld] = R S^-1 g (:204), C_dev = chol(R + 1e-11 I) (:205), both N x ld lower with
+ * zeroed strict upper triangle; info_dev[0/1] = dpotrf status of the two factorisations (no jitter retry here: the
+ * Python mirror applies kcGP.tools.jitchol semantics by re-calling with jitter).
+ */
+size_t gpmc_aux_workspace_bytes(int N);
+int gpmc_aux_var_model(const double *K_dev, int N, int ld, const double *S_dev, const double *g_dev, double *L_dev,
+                       double *m_dev, double *C_dev, int *info_dev, void *ws_dev, size_t ws_bytes, void *stream);
+
+/*
+ * Forward substitution L x = b for B right-hand sides rhs_dev[B][ldv] (strideL = 0: one shared L) -- the triangular
+ * solves of tools.solve_chol (sliceSample.py:258) and inf_mcmc (:269).  quad_dev (optional) receives
+ * log N(b; 0, L L^T) = -(0.5 x.x + sum log L_ii + 0.5 N log 2 pi).
+ */
+int gpmc_trsv_lower_batched(const double *L_dev, int N, int ld, long long strideL, const double *rhs_dev, int ldv, int B,
+                            double *out_dev, double *quad_dev, void *stream);
+
+/*
+ * Rectangular cross-covariance K(x, z) for prediction: covK.RBF.getCovMatrix(x=, z=, mode='cross'), sliceSample.py:263.
+ * x_dev[N,D], z_dev[M,D], one hyper-parameter row hyp_dev[P]; out_dev[N][ld], ld >= M.
+ */
+int gpmc_cov_cross(const double *x_dev, int N, const double *z_dev, int M, int D, const double *hyp_dev, int P, int kind,
+                   double *out_dev, int ld, void *stream);
+
+/*
+ * likK.TruncatedGauss2.evaluate(y=y-my, mu=mu_b) for B latent vectors (sliceSample.py:50,62,118,143; ASSUMPTION-1):
+ * out[b] = sum_i log TN(y_i - my; mu_b[i], sn_b, [lower, upper]).  mu_dev[B][ldmu], sn_dev[B].
+ */
+int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ldmu, int N, int B, const double *sn_dev,
+                    double lower, double upper, double *out_dev, void *stream);
+
 /* Kernel tuning knobs for experiments (key 0: DMMA tile kernel variant, 0 = 8 warps 64x32, 1 = 16 warps 32x32). */
 int gpmc_set_tuning(int key, int value);
 

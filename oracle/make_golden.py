@@ -134,6 +134,27 @@ def chain_case(n=64, iters=40, start_iter=480, seed=500):
                 ref_histF=histF, ref_histHyp=histHyp, ref_trips=trips)
 
 
+class _ZeroMean(object):
+    def getMean(self, x):
+        return np.zeros((x.shape[0], 1))
+
+
+def infmcmc_case(n=64, ns=17, n_samples=5, seed=808):
+    """The reference's own ``inf_mcmc`` (``sliceSample.py:234-284``) under the shim, on a small synthetic model."""
+    import types
+    x, y = _series(n)
+    rs = np.random.RandomState(seed)
+    xs = np.sort(rs.uniform(0, n, size=(ns, 1)), axis=0)
+    hyp = np.asarray([4.2, 3.1, 1.7])
+    f = (y - y.mean())[:, None] * 0.6 + 0.3 * rs.standard_normal((n, n_samples))
+    model = types.SimpleNamespace(x=x, y=y.reshape(-1, 1), xs=xs, meanfunc=_ZeroMean(),
+                                  covfunc=kcgp_shim.RBF(np.log(hyp[0]), np.log(hyp[1])),
+                                  likfunc=kcgp_shim.TruncatedGauss2(upper=100 - y.mean(), lower=0 - y.mean(), log_sigma=np.log(hyp[2])))
+    mod = rl.load_literal(fresh=True)
+    ym, lw, up, Fs2 = mod.inf_mcmc(f, model)
+    return dict(x=x, y=y, xs=xs, hyp=hyp, f=f, ref_ym=ym, ref_lw=lw, ref_up=up, ref_Fs2=Fs2)
+
+
 def main():
     if not rl.available():
         sys.exit('reference tree not present: fixtures can only be generated in the build container')
@@ -157,6 +178,8 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, 'loglik_ard.npz'), n_cases=len(rows),
                         **{'%s_%d' % (k, i): v for i, r in enumerate(rows) for k, v in r.items()})
     print('loglik_ard: %d cases' % len(rows))
+    np.savez_compressed(os.path.join(GOLDEN, 'infmcmc_N64.npz'), **infmcmc_case())
+    print('infmcmc_N64 written')
     ch = chain_case()
     np.savez_compressed(os.path.join(GOLDEN, 'chain_N64.npz'), **ch)
     print('chain_N64: trips mean %.2f max %d; final hyp %s' % (ch['ref_trips'].mean(), ch['ref_trips'].max(), ch['ref_histHyp'][:, -1]))

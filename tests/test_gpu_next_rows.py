@@ -1,0 +1,147 @@
+"""SURVEY 8f "next" rows and the kcGP seam (8b): GPU-backed stand-ins for covK / tools / likK, the stand-alone
+aux_var_model, inf_mcmc, elliptical_slice and the Framework caller loop.  B200 only."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def shim():
+    from oracle import kcgp_shim
+    return kcgp_shim
+
+
+def test_covK_modes_match_shim(gp, shim):
+    rs = np.random.RandomState(1)
+    x = np.sort(rs.uniform(0, 50, size=(90, 1)), axis=0)
+    z = rs.uniform(0, 50, size=(23, 1))
+    a, b = np.log(3.3), np.log(2.2)
+    ours, ref = gp.kcGP.covK.RBF(a, b), shim.RBF(a, b)
+    np.testing.assert_allclose(ours.getCovMatrix(x=x, mode='train'), ref.getCovMatrix(x=x, mode='train'), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(ours.getCovMatrix(x=x, z=z, mode='cross'), ref.getCovMatrix(x=x, z=z, mode='cross'), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(ours.getCovMatrix(z=z, mode='self_test'), np.full((23, 1), np.exp(2 * b)), rtol=1e-15)
+    xa = rs.uniform(0, 10, size=(40, 3))
+    la = list(np.log([1.5, 2.5, 4.0]))
+    np.testing.assert_allclose(gp.kcGP.covK.RBFard(log_ell_list=la, log_sigma=b).getCovMatrix(x=xa, mode='train'),
+                               shim.RBFard(log_ell_list=la, log_sigma=b).getCovMatrix(x=xa, mode='train'), rtol=1e-12, atol=1e-300)
+
+
+def test_tools_jitchol_and_solve_chol(gp, shim):
+    rs = np.random.RandomState(2)
+    n = 150
+    M = rs.standard_normal((n, n))
+    A = M @ M.T + n * np.eye(n)
+    L = gp.kcGP.tools.jitchol(A)
+    Lr = shim.jitchol(A)
+    np.testing.assert_allclose(L, Lr, rtol=1e-11, atol=1e-12)
+    assert np.all(np.triu(L, 1) == 0)
+    B = rs.standard_normal((n, 4))
+    np.testing.assert_allclose(gp.kcGP.tools.solve_chol(L.T, B), shim.solve_chol(Lr.T, B), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gp.kcGP.tools.solve_chol(L.T, B[:, 0]), shim.solve_chol(Lr.T, B[:, 0]), rtol=1e-9, atol=1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.kcGP.tools.jitchol(-np.eye(8))
+
+
+def test_likK_truncated_gauss2(gp, shim):
+    rs = np.random.RandomState(3)
+    n = 333
+    y = rs.uniform(-40, 8, size=n)
+    mu = y + rs.standard_normal(n)
+    for sn in (0.3, 2.0, 7.5):
+        ours = gp.kcGP.likK.TruncatedGauss2(upper=8.8, lower=-91.2, log_sigma=np.log(sn))
+        ref = shim.TruncatedGauss2(upper=8.8, lower=-91.2, log_sigma=np.log(sn))
+        a, b = ours.evaluate(y=y, mu=mu), ref.evaluate(y=y, mu=mu)
+        assert abs(a - b) <= 1e-12 * abs(b)
+        ours.sn = 1.1; ref.sn = 1.1                       # mutable natural-scale sn (sliceSample.py:142)
+        assert abs(ours.evaluate(y=y, mu=mu) - ref.evaluate(y=y, mu=mu)) <= 1e-12 * abs(b)
+    Ymu, Lo, Up = ours.evaluate(mu=mu[:5, None], s2=np.full((5, 1), 0.4))
+    Ymr, Lr, Ur = ref.evaluate(mu=mu[:5, None], s2=np.full((5, 1), 0.4))
+    np.testing.assert_allclose(Ymu, Ymr, rtol=1e-13)
+    np.testing.assert_allclose(Up, Ur, rtol=1e-13)
+
+
+def test_aux_var_model_standalone(gp, shim):
+    """aux_var_model(f, K, sn, g) with a caller-supplied K (sliceSample.py:165-207 contract)."""
+    from oracle import sds_oracle as so
+    n = 200
+    x, y = gp.synthetic.ih45_series(n)
+    K = shim.RBF(np.log(4.0), np.log(6.0)).getCovMatrix(x=x, mode='train')
+    f = 0.5 * (y - y.mean())
+    np.random.seed(5)
+    g, KS, m, C, L = gp.kcMCMC.sliceSample.aux_var_model(f, K, 1.3)
+    np.random.seed(5)
+    zz = np.random.standard_normal(n)
+    go, KSo, mo, Co, Lo = so.aux_var_model(f, K, 1.3, z=zz, r_form='reduced')
+    np.testing.assert_allclose(g, go, rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(KS, KSo, rtol=1e-15)
+    np.testing.assert_allclose(L, Lo, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(m, mo, rtol=1e-8, atol=1e-9)
+    assert np.all(np.triu(C, 1) == 0) and np.all(np.triu(L, 1) == 0)
+    # C is the Cholesky factor of R + 1e-11 I (compared through the product: C itself has condition ~1e5.5)
+    R = Co @ Co.T
+    assert np.abs(C @ C.T - R).max() < 1e-10 * np.abs(R).max()
+    # g passed in is returned as is (sliceSample.py:192,207)
+    g2, _, m2, _, _ = gp.kcMCMC.sliceSample.aux_var_model(f, K, 1.3, g=g)
+    assert g2 is g and np.allclose(m2, m, rtol=1e-12, atol=1e-12)
+
+
+def test_inf_mcmc_matches_reference_fixture(gp):
+    z = np.load(os.path.join(GOLDEN, 'infmcmc_N64.npz'))
+    x, y, xs, hyp, f = z['x'], z['y'], z['xs'], z['hyp'], z['f']
+    zero = types.SimpleNamespace(getMean=lambda a: np.zeros((a.shape[0], 1)))
+    model = types.SimpleNamespace(x=x, y=y.reshape(-1, 1), xs=xs, meanfunc=zero,
+                                  covfunc=gp.kcGP.covK.RBF(np.log(hyp[0]), np.log(hyp[1])),
+                                  likfunc=gp.kcGP.likK.TruncatedGauss2(upper=100 - y.mean(), lower=0 - y.mean(), log_sigma=np.log(hyp[2])))
+    ym, lw, up, Fs2 = gp.kcMCMC.sliceSample.inf_mcmc(f, model)
+    np.testing.assert_allclose(ym, z['ref_ym'], rtol=1e-9)
+    np.testing.assert_allclose(lw, z['ref_lw'], rtol=1e-8)
+    np.testing.assert_allclose(up, z['ref_up'], rtol=1e-8)
+    np.testing.assert_allclose(Fs2, z['ref_Fs2'], rtol=1e-8, atol=1e-12)
+
+
+def test_elliptical_slice_contract(gp):
+    n = 120
+    x, y = gp.synthetic.ih45_series(n)
+    hyp = np.array([5.0, 4.0, 2.5])
+    f = 0.8 * (y - y.mean())
+    np.random.seed(9)
+    pf = gp.kcMCMC.sliceSample.elliptical_slice(f, x, y, hyp)
+    assert pf.shape == f.shape and np.all(np.isfinite(pf)) and not np.array_equal(pf, f)
+    lik = gp.kcGP.likK.TruncatedGauss2(upper=100 - y.mean(), lower=-y.mean(), log_sigma=np.log(hyp[2]))
+    assert np.isfinite(lik.evaluate(y=y - y.mean(), mu=pf))
+
+
+def test_framework_loop_matches_oracle_on_the_global_stream(gp, tmp_path):
+    """Framework.runSimulMCMC (framework.py:59-77) with the global numpy stream seeded: same decisions as the oracle
+    consuming the same stream; CSV output in the reference's format."""
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    n, iters = 80, 4
+    x, y = gp.synthetic.ih45_series(n)
+    fw = gp.framework.Framework(np.column_stack([y, x]))
+    np.random.seed(2024)
+    histF, histHyp = fw.runSimulMCMC(iters)
+    assert histF.shape == (n, iters) and histHyp.shape == (3, iters)
+    rs = np.random.RandomState(2024)
+    fcur, hcur = np.zeros(n), np.array([1., 10., 1.2])
+    for i in range(iters):
+        zz, v, u0 = rs.standard_normal(n), rs.random_sample(3), rs.random_sample()
+        state = rs.get_state()
+        U = rs.random_sample((256, 3))
+        tr = so.SweepTrace()
+        fcur, hcur = so.surrogate_slice_sampling(fcur, x, y, hcur, np.array([10., 10., 5.]), i, Tape(zz, v, u0, U), trace=tr, r_form='reduced')
+        rs.set_state(state)
+        rs.random_sample((tr.n_trips, 3))
+        np.testing.assert_allclose(histHyp[:, i], hcur, rtol=1e-9)
+        fcur = histF[:, i].copy()          # follow the device chain's f (f' is resolved to ~1e-3 only)
+    fw.output(gap=2, histHyp=histHyp.T, histF=histF, out_dir=str(tmp_path))
+    rows = open(os.path.join(str(tmp_path), 'hypGap2.csv')).read().splitlines()
+    assert rows[0] == 'll,sf2,sn' and len(rows) == iters + 1
+    head = open(os.path.join(str(tmp_path), 'fGap2.csv')).readline().strip().split(',')
+    assert head == [str(i) for i in range(1, iters + 1)] + ['x', 'y']

@@ -245,3 +245,19 @@ def test_loglik_edge_cases(gp, so):
     # N = 1
     ll, info = gp.ops.loglik_host(np.zeros((1, 1)), np.array([[0.7]]), np.array([[1., 2., 0.5]]))
     assert abs(ll[0] - so.loglik_unit(np.zeros((1, 1)), np.array([0.7]), np.array([1., 2., 0.5]))) < 1e-13
+
+
+def test_loglik_large_single_matrix(gp, so):
+    """BASELINE config 4 shape: one N=16384 matrix (2 GiB): g-homogeneity property plus a direct oracle check."""
+    n = 16384
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    rs = np.random.RandomState(16384)
+    H = np.array([[5.0, 4.0, 2.5]] * 3)
+    g = 2.5 * rs.standard_normal(n)
+    G = np.stack([g, np.zeros(n), -2.0 * g])
+    ll, info = gp.ops.loglik_host(x, G, H)
+    assert np.all(info == 0)
+    q = ll[0] - ll[1]
+    assert abs((ll[2] - ll[1]) - 4.0 * q) <= 1e-11 * abs(ll[2])
+    ref = so.loglik_unit(x, g, H[0], form='trsv')
+    assert abs(ll[0] - ref) <= RTOL_LOGLIK * abs(ref)

@@ -200,3 +200,31 @@ def test_posterior_statistics_match_oracle_chains(gp):
         print('dim %d: device %.3f oracle %.3f z=%.2f (trips mean %.2f)' % (d, dev[:, d].mean(), ora[:, d].mean(), zscore, trips.mean()))
         assert zscore < 4.5
     assert np.all(hist[:, 2, :] == H0[:, 2:3])                     # noise frozen while iter < 500
+
+
+def test_ard_sweep_matches_oracle(gp):
+    """BASELINE config 3 style (ARD kernel, P = D + 2 hyper-parameters; not in the reference, which hard-codes
+    P = 3 at sliceSample.py:124-125,159): the generalised sweep against the generalised oracle on a tape."""
+    import torch
+    from gpmc_b200 import ops
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    n, d, B = 96, 3, 4
+    x, y = gp.synthetic.ard_inputs(n, d)
+    F0, H0 = gp.synthetic.chain_states(B, n, n_ell=d)
+    scale = np.array([10.0] * d + [10.0, 5.0])
+    P = d + 2
+    for it in (0, 700):
+        rs = np.random.RandomState(31 + it)
+        z, v, u0, U = rs.standard_normal((B, n)), rs.random_sample((B, P)), rs.random_sample(B), rs.random_sample((B, 48, P))
+        F = torch.tensor(F0.copy()).cuda()
+        H = torch.tensor(H0.copy()).cuda()
+        nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it, tape=ops.Tape(z, v, u0, U), max_trips=48)
+        assert np.all(st.cpu().numpy() == 0)
+        for c in range(B):
+            tr = so.SweepTrace()
+            of, oh = so.surrogate_slice_sampling(F0[c], x, y, H0[c], scale, it, Tape(z[c], v[c], u0[c], U[c]), trace=tr, r_form='reduced')
+            assert int(nt[c].item()) == tr.n_trips
+            np.testing.assert_allclose(H.cpu().numpy()[c], oh, rtol=RTOL_HYP)
+            assert np.abs(F.cpu().numpy()[c] - of).max() < F_ABS_CAP
+            assert abs(float(ll[c].item()) - tr.propG_chol[-1]) <= 1e-9 * abs(tr.propG_chol[-1])
