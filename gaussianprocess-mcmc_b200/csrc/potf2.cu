@@ -81,19 +81,34 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
                 x[c] = (c == lane) ? 1.0 : 0.0;
             }
             int fail = 0;
+            // micro-blocks of 8 columns: inside a micro-block the pivot chain (shuffle -> rsqrt -> scale -> shuffle ->
+            // fma) only touches the micro-block's own columns; the remaining columns are updated afterwards in one
+            // sweep whose (column, multiplier) pairs are independent, so the critical path is 4 x 8 short steps
 #pragma unroll
-            for (int c = 0; c < PB; ++c) {
-                const double piv = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(piv > 0.0) && fail == 0) fail = j0 + k0 + c + 1;          // dpotf2: ajj <= 0 or NaN
-                const double rinv = rsqrt(piv);
-                const double d = piv * rinv;
-                a[c] = (lane == c) ? d : a[c] * rinv;                          // column c of L
-                x[c] = x[c] * rinv;                                            // column c of X = L^-T (rows <= c)
+            for (int q = 0; q < PB / 8; ++q) {
 #pragma unroll
-                for (int j = c + 1; j < PB; ++j) {
-                    const double ljc = __shfl_sync(0xffffffffu, a[c], j);
-                    a[j] = fma(-a[c], ljc, a[j]);
-                    x[j] = fma(-x[c], ljc, x[j]);
+                for (int c = q * 8; c < q * 8 + 8; ++c) {
+                    const double piv = __shfl_sync(0xffffffffu, a[c], c);
+                    if (!(piv > 0.0) && fail == 0) fail = j0 + k0 + c + 1;          // dpotf2: ajj <= 0 or NaN
+                    const double rinv = rsqrt(piv);
+                    const double d = piv * rinv;
+                    a[c] = (lane == c) ? d : a[c] * rinv;                          // column c of L
+                    x[c] = x[c] * rinv;                                            // column c of X = L^-T (rows <= c)
+#pragma unroll
+                    for (int j = c + 1; j < q * 8 + 8; ++j) {
+                        const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+                        a[j] = fma(-a[c], ljc, a[j]);
+                        x[j] = fma(-x[c], ljc, x[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = q * 8 + 8; j < PB; ++j) {
+#pragma unroll
+                    for (int c = q * 8; c < q * 8 + 8; ++c) {
+                        const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+                        a[j] = fma(-a[c], ljc, a[j]);
+                        x[j] = fma(-x[c], ljc, x[j]);
+                    }
                 }
             }
             // write back: L (lower incl. diagonal) and X (strict upper) into T; clean inverse Lc[c][k] = X[k][c]

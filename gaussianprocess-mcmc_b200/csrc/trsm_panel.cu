@@ -5,7 +5,7 @@
 // has condition ~1e11, and  A21 * inv(L11)  would lose cond(L11) * eps (measured: spurious "not positive definite"
 // pivots); substitution keeps the residual at eps * |X| |L11|.
 //
-// One CTA owns 128 rows of the panel.  Each of its 16 warps keeps 8 rows x 128 columns as FP64 DMMA accumulator
+// One CTA owns 64 rows of the panel (two CTAs per SM).  Each of its 8 warps keeps 8 rows x 128 columns as FP64 DMMA accumulator
 // fragments in registers for the whole kernel and, after the initial load of L11, never meets a block barrier.
 // The 128 columns are processed in four sub-blocks of 32:
 //   solve : substitution in the fragment layout itself -- column c of a row lives in one lane of the row's quad;
@@ -19,10 +19,10 @@
 
 namespace gpmc {
 
-constexpr int TP_ROWS = 128;
+constexpr int TP_ROWS = 64;                   // rows per CTA; two CTAs per SM overlap each other's load/store phases
 constexpr int TP_B = 34;                      // stride of L blocks and of the staged sub-block: the substitution's
                                               // L[j][c] reads (j = 2*fk + ..) fall in 4 distinct bank groups
-constexpr int TP_THREADS = 512;               // 16 warps x 8 rows: the kernel is latency bound, warps hide it
+constexpr int TP_THREADS = 256;               // 8 warps x 8 rows, 2 CTAs per SM: the kernel is latency bound, warps hide it
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
 constexpr int TP_SMEM = (TP_ROWS * TP_B + 10 * TP_LBLK + NB) * (int)sizeof(double);    // 130,048 B
 
@@ -35,7 +35,7 @@ __device__ __forceinline__ void dmma884_t(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 1)
+__global__ void __launch_bounds__(TP_THREADS, 2)
 trsm_panel_kernel(BatchView A, int n, int j0)
 {
     extern __shared__ __align__(16) double sm[];
