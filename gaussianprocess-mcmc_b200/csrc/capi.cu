@@ -128,10 +128,10 @@ size_t gpmc_workspace_bytes(int op, int N, int D, int B)
     }
     if (op == GPMC_OP_LOGLIK) {
         const LoglikLayout l = loglik_layout(N, B);
-        // recommended wave: up to 256 items, capped at 48 GiB
-        size_t wave = std::min<size_t>(B, 256);
+        // recommended wave: as many items as fit in 48 GiB (large waves amortise the panel kernels' latency and the
+        // per-wave host synchronisation of the jitter check), at most 8192
         const size_t cap = (size_t)48 << 30;
-        while (wave > 1 && wave * l.per_item_bytes > cap) wave /= 2;
+        size_t wave = std::min<size_t>(std::min<size_t>(B, 8192), std::max<size_t>(1, cap / l.per_item_bytes));
         return l.fixed_bytes + wave * l.per_item_bytes;
     }
     return 0;

@@ -157,39 +157,58 @@ int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows,
 }
 
 // ------------------------------------------------------------------ blocked Cholesky sequencing
-// Left-looking by block columns of NB: update the block column with everything to its left (DMMA GEMM),
-// factor the diagonal block (+ its inverse for inverse_sequence), solve the rows below by blocked substitution.
-int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
-                   int zero_upper, cudaStream_t s)
+// Block columns of NB.  With many matrices per launch the schedule is purely LEFT-LOOKING: update the block column
+// with everything to its left (one long-K DMMA GEMM), factor the diagonal block (+ its inverse for
+// inverse_sequence), solve the rows below by blocked substitution.  When one launch would not fill the chip (few
+// matrices: B * N/128 < 1024, e.g. the single N=16384 matrix of BASELINE config 4) the columns are grouped in WINDOWS:
+// left-looking inside a window (contraction limited to the window), then ONE right-looking trailing update
+// A22 -= L21 L21^T with thousands of tiles and K = window -- the classic DMMA trailing update.
+static int potrf_window_for(int n, int B)
 {
     const int nt = (n + NB - 1) / NB;
+    if ((long long)B * nt >= 1024) return 0;
+    return n >= 8192 ? 1024 : 512;
+}
+
+int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
+                   int zero_upper_flag, cudaStream_t s)
+{
+    const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
-    for (int j = 0; j < nt; ++j) {
-        const int j0 = j * NB;
-        const int width = std::min(NB, n - j0);
-        double *Wj = W + (size_t)j * w_step;
-        if (j > 0) {
+    const int wlen = window > 0 ? window : n;
+    for (int w0 = 0; w0 < n; w0 += wlen) {
+        const int w1 = std::min(n, w0 + wlen);
+        for (int j0 = w0; j0 < w1; j0 += NB) {
+            const int width = std::min(NB, n - j0);
+            double *Wj = W + (size_t)(j0 / NB) * w_step;
+            if (j0 > w0) {
+                GemmArgs g{};
+                g.C = A; g.A = self; g.B = self;
+                g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
+                g.ar0 = j0; g.br0 = j0; g.k0 = w0; g.bk0 = w0; g.klen = j0 - w0;
+                g.epi = EPI_SUB;
+                int rc = launch_gemm(g, B, KC_GEMM, s);
+                if (rc) return rc;
+            }
+            int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s);
+            if (rc) return rc;
+            if (j0 + NB < n) {
+                rc = launch_trsm_panel(A, n, j0, B, s);
+                if (rc) return rc;
+            }
+        }
+        if (w1 < n) {
             GemmArgs g{};
             g.C = A; g.A = self; g.B = self;
-            g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
-            g.ar0 = j0; g.br0 = j0; g.k0 = 0; g.bk0 = 0; g.klen = j0;
+            g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = n - w1;
+            g.ar0 = w1; g.br0 = w1; g.k0 = w0; g.bk0 = w0; g.klen = w1 - w0;
+            g.lower_only = 1;
             g.epi = EPI_SUB;
             int rc = launch_gemm(g, B, KC_GEMM, s);
             if (rc) return rc;
         }
-        int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper, B, s);
-        if (rc) return rc;
-        if (j0 + NB < n) {
-            rc = launch_trsm_panel(A, n, j0, B, s);
-            if (rc) return rc;
-        }
     }
-    if (zero_upper) {
-        dim3 blk(32, 8);
-        dim3 grid((n + 31) / 32, (n + 7) / 8, B);
-        zero_upper_kernel<<<grid, blk, 0, s>>>(A, n);
-        GPMC_LAUNCH_CHECK();
-    }
+    if (zero_upper_flag) return zero_upper(A, n, B, s);
     return 0;
 }
 
