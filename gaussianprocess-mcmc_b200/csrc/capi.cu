@@ -89,7 +89,8 @@ static LoglikLayout loglik_layout(int N, int B)
     l.per_item_bytes = l.mat_elems * sizeof(double) + (size_t)NB * NB * sizeof(double);
     l.fixed_bytes = align_up((size_t)B * sizeof(double), 256)      // jitter
                     + align_up((size_t)B * sizeof(int), 256)       // map
-                    + 256;                                         // count
+                    + 256                                          // count
+                    + align_up((size_t)32 * l.ld * sizeof(double), 256);   // z scratch of the small-batch solve
     return l;
 }
 
@@ -236,6 +237,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
     double *jit_dev = (double *)wp; wp += align_up((size_t)B * sizeof(double), 256);
     int *map_dev = (int *)wp; wp += align_up((size_t)B * sizeof(int), 256);
     wp += 256;
+    double *zscratch = (double *)wp; wp += align_up((size_t)32 * l.ld * sizeof(double), 256);
     const size_t wave_cap = (ws_bytes - l.fixed_bytes) / l.per_item_bytes;
     const int wave = (int)std::min<size_t>(wave_cap, (size_t)B);
     double *mats = (double *)wp;
@@ -293,7 +295,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                 GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
             }
         }
-        rc = launch_solve_reduce(A, N, g_w, nullptr, N, nullptr, loglik_dev + s0, info_w, nb, s);
+        rc = launch_solve_reduce(A, N, g_w, nullptr, N, (nb < 32 && (N & 1) == 0) ? zscratch : nullptr, loglik_dev + s0, info_w, nb, s);
         if (rc) return rc;
     }
     return 0;

@@ -135,14 +135,83 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ va, const dou
     }
 }
 
+// ---- few matrices (B < 32): the one-CTA-per-matrix walk above would leave the chip idle (N=16384: 1 GiB read by one
+// SM), so the same substitution is run RIGHT-LOOKING in launches: solve the 128x128 diagonal block (the kernel above
+// on a sub-view), then every row below subtracts its 128-column contribution in parallel over the whole chip.
+__global__ void __launch_bounds__(256)
+gemv_sub_kernel(BatchView L, int n, int j0, const double *__restrict__ z, double *__restrict__ w, int ldv, const int *__restrict__ info)
+{
+    const int b = blockIdx.y;
+    if (L.count && b >= *L.count) return;
+    const int m = batch_item(L, b);
+    if (info && info[m] != 0) return;
+    const double *Lb = L.base + (size_t)m * L.stride;
+    const double *zv = z + (size_t)m * ldv + j0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double2 z0 = *reinterpret_cast<const double2 *>(zv + 2 * lane);
+    const double2 z1 = *reinterpret_cast<const double2 *>(zv + 64 + 2 * lane);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = j0 + NB + blockIdx.x * 32 + warp * 4 + rr;
+        if (r >= n) break;
+        const double *row = Lb + (size_t)r * L.ld + j0;
+        const double2 l0 = *reinterpret_cast<const double2 *>(row + 2 * lane);
+        const double2 l1 = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
+        double acc = fma(l0.x, z0.x, fma(l0.y, z0.y, fma(l1.x, z1.x, l1.y * z1.y)));
+        acc = warp_sum(acc);
+        if (lane == 0) w[(size_t)m * ldv + r] -= acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+quad_logdet_kernel(BatchView L, int n, const double *__restrict__ z, int ldv, double *__restrict__ loglik, const int *__restrict__ info)
+{
+    const int b = blockIdx.x;
+    if (L.count && b >= *L.count) return;
+    const int m = batch_item(L, b);
+    __shared__ double rq[8], rl[8];
+    if (info && info[m] != 0) { if (threadIdx.x == 0) loglik[m] = nan(""); return; }
+    const double *Lb = L.base + (size_t)m * L.stride;
+    double q = 0.0, ld = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double zi = z[(size_t)m * ldv + i];
+        q = fma(zi, zi, q);
+        ld += log(Lb[(size_t)i * L.ld + i]);
+    }
+    q = warp_sum(q); ld = warp_sum(ld);
+    if ((threadIdx.x & 31) == 0) { rq[threadIdx.x >> 5] = q; rl[threadIdx.x >> 5] = ld; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double qs = 0.0, ls = 0.0;
+        for (int w = 0; w < 8; ++w) { qs += rq[w]; ls += rl[w]; }
+        loglik[m] = -(qs / 2.0 + ls + n * 1.8378770664093453 / 2.0);
+    }
+}
+
 int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, int ldv, double *zout,
                         double *loglik, const int *info, int B, cudaStream_t s)
 {
     if (B <= 0) return 0;
     if (n > SOLVE_MAX_N) { set_error("solve_reduce: n=%d exceeds %d", n, SOLVE_MAX_N); return GPMC_EINVAL; }
+    GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (B < 32 && n >= 1024 && zout && !b && (n % NB) == 0 && (ldv & 1) == 0) {
+        // right-looking in launches; zout doubles as the working right-hand side
+        GPMC_CUDA_CHECK(cudaMemcpy2DAsync(zout, (size_t)ldv * 8, a, (size_t)ldv * 8, (size_t)n * 8, B, cudaMemcpyDeviceToDevice, s));
+        const int smem128 = (NB + SB * SBP + 16) * (int)sizeof(double);
+        prof_begin(KC_SOLVE, s);
+        for (int j0 = 0; j0 < n; j0 += NB) {
+            BatchView D{L.base + (size_t)j0 * L.ld + j0, L.stride, L.ld, L.map, L.count};
+            solve_reduce_kernel<<<B, SOLVE_THREADS, smem128, s>>>(D, NB, zout + j0, nullptr, ldv, zout + j0, nullptr, info);
+            if (j0 + NB < n)
+                gemv_sub_kernel<<<dim3((n - j0 - NB + 31) / 32, B), 256, 0, s>>>(L, n, j0, zout, zout, ldv, info);
+        }
+        if (loglik) quad_logdet_kernel<<<B, 256, 0, s>>>(L, n, zout, ldv, loglik, info);
+        prof_end(KC_SOLVE, s);
+        GPMC_LAUNCH_CHECK();
+        return 0;
+    }
     const int npad = (n + SB - 1) / SB * SB;
     const int smem = (npad + SB * SBP + 16) * (int)sizeof(double);
-    GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     prof_begin(KC_SOLVE, s);
     solve_reduce_kernel<<<B, SOLVE_THREADS, smem, s>>>(L, n, a, b, ldv, zout, loglik, info);
     prof_end(KC_SOLVE, s);
