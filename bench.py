@@ -25,6 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# ncu-measured DRAM bytes per eval of the update kernel, keyed by (N, panel width); see profiles/
+TRAFFIC_BYTES_PER_EVAL = {(4096, 128): 827.98e6}
 METRIC = 'GP log-lik evals/sec (N=4096, batched chains)'
 UNIT = 'evals/s'
 
@@ -270,17 +272,18 @@ def run_b200(args):
     gemm_ms, gemm_launches = prof['gemm_update']
     achieved = evals_timed * chol_flops / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None
     # executed MACs of the update kernel: full 128-row tiles of every block column
-    nt = (n + 127) // 128
-    exec_flops = sum(2.0 * ((n - j * 128 + 127) // 128 * 128) * 128 * (j * 128) for j in range(1, nt))
+    nb = gp._lib.load().gpmc_panel_width()                          # block-column width of this build (64 or 128)
+    nt = (n + nb - 1) // nb
+    exec_flops = sum(2.0 * ((n - j * nb + 127) // 128 * 128) * nb * (j * nb) for j in range(1, nt))
     peak = peaks.get('cublas_dgemm_8192_tflops')
     roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
         'frac': (achieved / peak) if (achieved and peak) else None,
-        # DRAM bytes per eval of the dominant kernel (the 31 update launches of one N=4096 factorisation), from the ncu
-        # capture profiles/r01c_gemm31.csv (dram__bytes_read.sum + dram__bytes_write.sum, 16 chains): 828 MB measured
-        # vs 845 MB algorithmic (every L row read once per block column + the block column read and written once)
-        'traffic': 827.98e6 if n == 4096 else None, 'traffic_unit': 'bytes per eval (update kernel)',
-        'traffic_algorithmic': sum((n - j * 128) * (j * 128) * 8 + 2 * (n - j * 128) * 128 * 8 for j in range(1, (n + 127) // 128)),
+        # DRAM bytes per eval of the dominant kernel (all update launches of one factorisation) from an ncu capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/), next to the algorithmic bytes (every L row read
+        # once per block column + the block column read and written once)
+        'traffic': TRAFFIC_BYTES_PER_EVAL.get((n, nb)), 'traffic_unit': 'bytes per eval (update kernel)',
+        'traffic_algorithmic': sum((n - j * nb) * (j * nb) * 8 + 2 * (n - j * nb) * nb * 8 for j in range(1, nt)),
         'peak_source': 'measured in this run: cuBLAS DGEMM 8192^3 FP64 (MEASURED_PEAKS.json has no FP64 figure); '
                        'nominal B200 FP64 tensor 40 TFLOP/s',
         'what': 'batched blocked Cholesky (TMA-staged DMMA update kernel + potf2 + panel solve launches), N^3/3 flop per eval '

@@ -25,6 +25,7 @@ _sz = ctypes.c_size_t
 # name -> (restype, argtypes); every symbol include/gpmc.h declares
 SIGNATURES = {
     'gpmc_version': (_i, []),
+    'gpmc_panel_width': (_i, []),
     'gpmc_last_error': (ctypes.c_char_p, []),
     'gpmc_device_info': (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz)]),
     'gpmc_workspace_bytes': (_sz, [_i, _i, _i, _i]),

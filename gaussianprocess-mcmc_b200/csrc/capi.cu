@@ -101,6 +101,7 @@ using namespace gpmc;
 extern "C" {
 
 int gpmc_version(void) { return GPMC_VERSION; }
+int gpmc_panel_width(void) { return NB; }
 const char *gpmc_last_error(void) { return g_err; }
 
 int gpmc_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes)

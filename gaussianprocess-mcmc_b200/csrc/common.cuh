@@ -7,7 +7,11 @@
 
 namespace gpmc {
 
-constexpr int NB = 128;            // panel width / tile edge of the blocked Cholesky
+#ifndef GPMC_NB
+#define GPMC_NB 64
+#endif
+constexpr int NB = GPMC_NB;        // panel width of the blocked Cholesky (64 or 128)
+static_assert(NB == 64 || NB == 128, "panel width must be 64 or 128");
 constexpr int MAX_ELL = 8;         // max number of length-scales (ARD input dimension)
 
 // kernel classes for the profiling hooks (gpmc_profile_read)

@@ -18,10 +18,12 @@
 
 namespace gpmc {
 
-constexpr int PT = 132;                       // smem row stride (doubles): 4 mod 16 -> conflict-free DMMA fragments
+constexpr int PT = NB + 4;                    // smem row stride (doubles): 4 mod 16 -> conflict-free DMMA fragments
 constexpr int PB = 32;                        // inner block
 constexpr int PC = 36;                        // row stride of the clean 32x32 inverse
-constexpr int POTF2_THREADS = 256;
+constexpr int POTF2_THREADS = NB == 64 ? 128 : 256;
+constexpr int POTF2_WARPS = POTF2_THREADS / 32;
+constexpr int POTF2_CTAS = NB == 64 ? 2 : 1;
 constexpr int POTF2_SMEM = (NB * PT + PB * PC + NB) * (int)sizeof(double);
 
 __device__ __forceinline__ void dmma884_p(double &c0, double &c1, double a, double b)
@@ -31,7 +33,7 @@ __device__ __forceinline__ void dmma884_p(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(POTF2_THREADS, 1)
+__global__ void __launch_bounds__(POTF2_THREADS, POTF2_CTAS)
 potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info,
                  int zero_upper)
 {
@@ -52,7 +54,7 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     // stage the block with 16-byte cp.async pieces (all in flight at once), then fix up in shared memory:
     // strict upper = 0 (the identity's off-diagonal), rows/cols beyond the matrix = identity
     for (int e = tid; e < NB * (NB / 2); e += POTF2_THREADS) {
-        const int r = e >> 6, c2 = (e & 63) * 2;
+        const int r = e / (NB / 2), c2 = (e % (NB / 2)) * 2;
         if (r < nv && c2 <= r) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(&T[r * PT + c2]);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)r * ld + c2));
@@ -188,7 +190,7 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
                 const int rows_x = k0 + PB;                   // X part: rows [0, k0+32)
                 const int nrb = rows_x / 8 + (NB - c0) / 8;   // + L part: rows [c0, 128)
                 for (int rb = 0; rb < nrb; ++rb, ++u) {
-                    if ((u & 7) != warp) continue;
+                    if ((u % POTF2_WARPS) != warp) continue;
                     const int r0 = (rb < rows_x / 8) ? rb * 8 : c0 + (rb - rows_x / 8) * 8;
                     const bool diag_rows = (r0 >= k0) && (r0 < k0 + PB);
                     double af[8];

@@ -165,7 +165,7 @@ int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows,
 // A22 -= L21 L21^T with thousands of tiles and K = window -- the classic DMMA trailing update.
 static int potrf_window_for(int n, int B)
 {
-    const int nt = (n + NB - 1) / NB;
+    const int nt = (n + 127) / 128;                 // 128-row tiles of a block column
     if ((long long)B * nt >= 1024) return 0;
     return n >= 8192 ? 1024 : 512;
 }

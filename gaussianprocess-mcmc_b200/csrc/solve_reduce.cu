@@ -148,16 +148,20 @@ gemv_sub_kernel(BatchView L, int n, int j0, const double *__restrict__ z, double
     const double *Lb = L.base + (size_t)m * L.stride;
     const double *zv = z + (size_t)m * ldv + j0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double2 z0 = *reinterpret_cast<const double2 *>(zv + 2 * lane);
-    const double2 z1 = *reinterpret_cast<const double2 *>(zv + 64 + 2 * lane);
+    double2 zc[NB / 64];
+#pragma unroll
+    for (int q = 0; q < NB / 64; ++q) zc[q] = *reinterpret_cast<const double2 *>(zv + q * 64 + 2 * lane);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
         const int r = j0 + NB + blockIdx.x * 32 + warp * 4 + rr;
         if (r >= n) break;
         const double *row = Lb + (size_t)r * L.ld + j0;
-        const double2 l0 = *reinterpret_cast<const double2 *>(row + 2 * lane);
-        const double2 l1 = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
-        double acc = fma(l0.x, z0.x, fma(l0.y, z0.y, fma(l1.x, z1.x, l1.y * z1.y)));
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB / 64; ++q) {
+            const double2 l = *reinterpret_cast<const double2 *>(row + q * 64 + 2 * lane);
+            acc = fma(l.x, zc[q].x, fma(l.y, zc[q].y, acc));
+        }
         acc = warp_sum(acc);
         if (lane == 0) w[(size_t)m * ldv + r] -= acc;
     }

@@ -13,7 +13,7 @@
 //           entries read from shared memory (no explicit inverse anywhere)
 //   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA; the solved sub-block is
 //           staged through the warp's own shared-memory rows to become A fragments (and goes out to global).
-// L11 is kept as its ten lower 32x32 blocks, staged with cp.async.
+// L11 is kept as its lower 32x32 blocks, staged with cp.async.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
@@ -24,7 +24,10 @@ constexpr int TP_B = 34;                      // stride of L blocks and of the s
                                               // L[j][c] reads (j = 2*fk + ..) fall in 4 distinct bank groups
 constexpr int TP_THREADS = 256;               // 8 warps x 8 rows, 2 CTAs per SM: the kernel is latency bound, warps hide it
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
-constexpr int TP_SMEM = (TP_ROWS * TP_B + 10 * TP_LBLK + NB) * (int)sizeof(double);    // 130,048 B
+constexpr int TP_NSB = NB / 32;               // 32-column sub-blocks of the panel
+constexpr int TP_NLB = TP_NSB * (TP_NSB + 1) / 2;   // lower 32x32 blocks of L11
+constexpr int TP_NC8 = NB / 8;                // 8-column fragments per row
+constexpr int TP_SMEM = (TP_ROWS * TP_B + TP_NLB * TP_LBLK + NB) * (int)sizeof(double);
 
 __device__ __forceinline__ int lblk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
 
@@ -35,13 +38,13 @@ __device__ __forceinline__ void dmma884_t(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 2)
+__global__ void __launch_bounds__(TP_THREADS, NB == 64 ? 3 : 2)
 trsm_panel_kernel(BatchView A, int n, int j0)
 {
     extern __shared__ __align__(16) double sm[];
     double *R = sm;                               // [128][36] the sub-block being solved
     double *Lb = sm + TP_ROWS * TP_B;             // 10 lower blocks of L11
-    double *dinv = Lb + 10 * TP_LBLK;             // [128]
+    double *dinv = Lb + TP_NLB * TP_LBLK;             // [128]
     const int b = blockIdx.y;
     if (A.count && b >= *A.count) return;
     const int m = batch_item(A, b);
@@ -54,7 +57,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
 
     // L11 (rows/cols j0 .. j0+127), lower 32-blocks, 16-byte cp.async pieces (all in flight at once);
     // the strict upper part of diagonal blocks is never read
-    for (int e = tid; e < 10 * 32 * 16; e += TP_THREADS) {        // 16 pieces per block row
+    for (int e = tid; e < TP_NLB * 32 * 16; e += TP_THREADS) {        // 16 pieces per block row
         const int blk = e / (32 * 16), rem = e - blk * 32 * 16;
         const int r = rem / 16, c2 = (rem - r * 16) * 2;
         int bi = 0;
@@ -65,12 +68,12 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     }
     asm volatile("cp.async.commit_group;\n" ::);
     // this warp's 8 rows as accumulator fragments: acc[cb8] = row warp*8 + fr, cols cb8*8 + 2fk, +1
-    double acc[16][2];
+    double acc[TP_NC8][2];
     {
         const int r = warp * 8 + fr;
         const double *src = Ab + (size_t)(row0 + min(r, rows_valid - 1)) * ld + j0 + 2 * fk;
 #pragma unroll
-        for (int cb8 = 0; cb8 < 16; ++cb8) {
+        for (int cb8 = 0; cb8 < TP_NC8; ++cb8) {
             double2 v = make_double2(0.0, 0.0);
             if (r < rows_valid) v = *reinterpret_cast<const double2 *>(src + cb8 * 8);
             acc[cb8][0] = v.x;
@@ -87,7 +90,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     // From here on every warp works on its own 16 rows only (L and dinv are read-only): no block barriers.
     double *Rw = R + warp * 8 * TP_B;             // this warp's staging rows
 #pragma unroll
-    for (int sb = 0; sb < 4; ++sb) {
+    for (int sb = 0; sb < TP_NSB; ++sb) {
         const double *Ld = Lb + lblk_index(sb, sb) * TP_LBLK;
         // ---- solve the sub-block's 32 columns in fragment layout.  Column c lives in lane fk == (c%8)/2 of each
         //      row's quad; the solved value is broadcast inside the quad and every lane updates its own later columns.
@@ -117,12 +120,12 @@ trsm_panel_kernel(BatchView A, int n, int j0)
                     *reinterpret_cast<const double2 *>(&Rw[r * TP_B + c2]);
         }
         // ---- update the later columns:  acc[:, cb8] -= X[:, sb] * L[cb8 rows, sb cols]^T
-        if (sb < 3) {
+        if (sb < TP_NSB - 1) {
             double af[8];
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) af[ks] = -Rw[fr * TP_B + ks * 4 + fk];
 #pragma unroll
-            for (int cb8 = (sb + 1) * 4; cb8 < 16; ++cb8) {
+            for (int cb8 = (sb + 1) * 4; cb8 < TP_NC8; ++cb8) {
                 const double *Lq = Lb + lblk_index(cb8 >> 2, sb) * TP_LBLK + ((cb8 & 3) * 8 + fr) * TP_B + fk;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) dmma884_t(acc[cb8][0], acc[cb8][1], af[ks], Lq[ks * 4]);

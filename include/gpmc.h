@@ -61,6 +61,8 @@ extern "C" {
 #define GPMC_OP_SDS     3
 
 int gpmc_version(void);
+/* panel width (block-column width) of the blocked Cholesky this build was compiled with: 64 or 128 */
+int gpmc_panel_width(void);
 const char *gpmc_last_error(void);
 /* sm count, compute capability, total HBM bytes of the current device */
 int gpmc_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
