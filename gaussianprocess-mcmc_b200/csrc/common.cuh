@@ -8,7 +8,7 @@
 namespace gpmc {
 
 #ifndef GPMC_NB
-#define GPMC_NB 64
+#define GPMC_NB 128
 #endif
 constexpr int NB = GPMC_NB;        // panel width of the blocked Cholesky (64 or 128)
 static_assert(NB == 64 || NB == 128, "panel width must be 64 or 128");
