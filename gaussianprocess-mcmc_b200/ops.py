@@ -122,15 +122,18 @@ def loglik_batched(x, g, hyp, jitter_policy=JITTER_PYGPS, workspace=None, max_wa
     info = torch.empty((B,), dtype=torch.int32, device='cuda')
     if B == 0:
         return out, info
+    wsobj = workspace or _default_ws
     need = lib.gpmc_workspace_bytes(OP_LOGLIK, N, D, B if max_wave is None else min(B, max_wave))
-    if max_wave is None:
+    have = 0 if wsobj.buf is None else wsobj.buf.numel()
+    if max_wave is None and have < need:
+        # growing: never ask for more than 60 % of what is free (cudaMemGetInfo is slow, so only look when growing)
         free, _ = torch.cuda.mem_get_info()
-        have = 0 if (workspace or _default_ws).buf is None else (workspace or _default_ws).buf.numel()
         one = lib.gpmc_workspace_bytes(OP_LOGLIK, N, D, 1)
         need = max(one, min(need, (free + have) * 6 // 10))
-    ws = (workspace or _default_ws).get(torch, need)
+    ws = wsobj.get(torch, need)
+    use_bytes = need if max_wave is not None else ws.numel()       # max_wave: really limit the wave (tests)
     rc = lib.gpmc_loglik_batched(x.data_ptr(), N, D, g.data_ptr(), hyp.data_ptr(), B, P, kind_of(D, P), jitter_policy,
-                                 out.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+                                 out.data_ptr(), info.data_ptr(), ws.data_ptr(), use_bytes, _stream_ptr(torch))
     _lib.check(rc, 'gpmc_loglik_batched')
     return out, info
 
@@ -222,13 +225,14 @@ def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max
         tz, tv, tu, tU = (torch.tensor(a).cuda() for a in (tape.z, tape.v, tape.u0, tape.U))
         ttrips = tape.U.shape[1]
     wsobj = workspace or _default_ws
+    have = 0 if wsobj.buf is None else wsobj.buf.numel()
     if chains_per_wave is None:
-        free, _ = torch.cuda.mem_get_info()
-        have = 0 if wsobj.buf is None else wsobj.buf.numel()
-        budget = (free + have) * 6 // 10
         chains_per_wave = B
-        while chains_per_wave > 1 and lib.gpmc_sds_workspace_bytes(N, P, chains_per_wave) > budget:
-            chains_per_wave = (chains_per_wave + 1) // 2
+        if lib.gpmc_sds_workspace_bytes(N, P, B) > have:
+            free, _ = torch.cuda.mem_get_info()
+            budget = (free + have) * 6 // 10
+            while chains_per_wave > 1 and lib.gpmc_sds_workspace_bytes(N, P, chains_per_wave) > max(budget, have):
+                chains_per_wave = (chains_per_wave + 1) // 2
     ws = wsobj.get(torch, lib.gpmc_sds_workspace_bytes(N, P, min(B, chains_per_wave)))
     ptr = lambda t: None if t is None else t.data_ptr()
     rc = lib.gpmc_sds_sweep(x.data_ptr(), y.data_ptr(), N, D, F.data_ptr(), Hyp.data_ptr(), B, P, kind,

@@ -40,7 +40,9 @@ def time_loglik(n, B, ard=0, reps=3):
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'quick':
+    if len(sys.argv) > 1 and sys.argv[1] == 'c2':
+        rows = [time_loglik(2048, 64, reps=10), time_loglik(200, 1, reps=20)]
+    elif len(sys.argv) > 1 and sys.argv[1] == 'quick':
         rows = [time_loglik(512, 4096, ard=4), time_loglik(16384, 1, reps=2)]
     else:
         rows = [time_loglik(200, 1), time_loglik(2048, 64), time_loglik(512, 4096, ard=4), time_loglik(16384, 1, reps=2),
