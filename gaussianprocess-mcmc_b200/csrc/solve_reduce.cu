@@ -167,6 +167,16 @@ gemv_sub_kernel(BatchView L, int n, int j0, const double *__restrict__ z, double
     }
 }
 
+// w[m] = a[m] for the (possibly mapped) items of the launch
+__global__ void copy_vec_mapped_kernel(BatchView L, int n, const double *__restrict__ a, double *__restrict__ w, int ldv)
+{
+    const int b = blockIdx.y;
+    if (L.count && b >= *L.count) return;
+    const int m = batch_item(L, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[(size_t)m * ldv + i] = a[(size_t)m * ldv + i];
+}
+
 __global__ void __launch_bounds__(256)
 quad_logdet_kernel(BatchView L, int n, const double *__restrict__ z, int ldv, double *__restrict__ loglik, const int *__restrict__ info)
 {
@@ -200,7 +210,7 @@ int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, in
     GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (B < 32 && n >= 1024 && zout && !b && (n % NB) == 0 && (ldv & 1) == 0) {
         // right-looking in launches; zout doubles as the working right-hand side
-        GPMC_CUDA_CHECK(cudaMemcpy2DAsync(zout, (size_t)ldv * 8, a, (size_t)ldv * 8, (size_t)n * 8, B, cudaMemcpyDeviceToDevice, s));
+        copy_vec_mapped_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(L, n, a, zout, ldv);   // items may be mapped slots
         const int smem128 = (NB + SB * SBP + 16) * (int)sizeof(double);
         prof_begin(KC_SOLVE, s);
         for (int j0 = 0; j0 < n; j0 += NB) {

@@ -228,3 +228,30 @@ def test_ard_sweep_matches_oracle(gp):
             np.testing.assert_allclose(H.cpu().numpy()[c], oh, rtol=RTOL_HYP)
             assert np.abs(F.cpu().numpy()[c] - of).max() < F_ABS_CAP
             assert abs(float(ll[c].item()) - tr.propG_chol[-1]) <= 1e-9 * abs(tr.propG_chol[-1])
+
+
+def test_mid_size_batch_equals_single_chain_runs(gp):
+    """N=1024 takes the small-batch code paths (windowed Cholesky schedule, multi-launch solve) once the active set
+    shrinks; a batch must still equal its chains run one by one (different trip counts -> mapped active lists)."""
+    import torch
+    from gpmc_b200 import ops
+    n, B = 1024, 5
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array(gp.synthetic.SCALE)
+
+    def run(lo, hi, sweeps=2):
+        F = torch.tensor(F0[lo:hi].copy()).cuda(); H = torch.tensor(H0[lo:hi].copy()).cuda()
+        trips = []
+        for it in range(sweeps):
+            nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it, seed=77, chain0=lo)
+            assert np.all(st.cpu().numpy() == 0)
+            trips.append(nt.cpu().numpy())
+        return F.cpu().numpy(), H.cpu().numpy(), np.stack(trips)
+    Fa, Ha, Ta = run(0, B)
+    assert len(set(Ta[0].tolist())) > 1 or len(set(Ta[1].tolist())) > 1      # chains really finish at different trips
+    for c in range(B):
+        Fc, Hc, Tc = run(c, c + 1)
+        assert np.array_equal(Tc[:, 0], Ta[:, c])
+        np.testing.assert_allclose(Hc[0], Ha[c], rtol=1e-12)
+        assert np.abs(Fc[0] - Fa[c]).max() < 5e-2
