@@ -39,7 +39,7 @@ def test_cov_assemble_iso_matches_cdist_form(gp, so, n):
         np.testing.assert_allclose(AS[b], KS, rtol=4e-15, atol=0)
 
 
-@pytest.mark.parametrize('n,d', [(32, 2), (300, 4), (512, 4)])
+@pytest.mark.parametrize('n,d', [(32, 2), (300, 4), (512, 4), (150, 5), (70, 8)])
 def test_cov_assemble_ard(gp, so, n, d):
     rs = np.random.RandomState(5)
     x = rs.uniform(0, 10, size=(n, d))
@@ -261,3 +261,29 @@ def test_loglik_large_single_matrix(gp, so):
     assert abs((ll[2] - ll[1]) - 4.0 * q) <= 1e-11 * abs(ll[2])
     ref = so.loglik_unit(x, g, H[0], form='trsv')
     assert abs(ll[0] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
+@pytest.mark.parametrize('cfg', [0, 1, 2, 3])
+def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
+    """The DMMA tile kernel exists in four variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
+    per SM, TMA-staged 128x64); all must give the same factor."""
+    import scipy.linalg
+    n = 700
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    H = np.array([[2.0, 7.0, 0.9], [6.0, 3.0, 2.0]])
+    try:
+        gp.ops.set_tuning(0, cfg)
+        A = gp.ops.cov_assemble(x, H, add_S=True)
+        A0 = A.cpu().numpy()[:, :, :n].copy()
+        info = gp.ops.potrf_batched(A, n=n)
+        G = np.random.RandomState(cfg).standard_normal((2, n))
+        ll, _ = gp.ops.loglik_host(x, G, H)
+    finally:
+        gp.ops.set_tuning(0, 3)
+    assert np.all(info.cpu().numpy() == 0)
+    L = A.cpu().numpy()[:, :, :n]
+    for b in range(2):
+        ref = scipy.linalg.cholesky(A0[b], lower=True)
+        np.testing.assert_allclose(L[b], ref, rtol=1e-10, atol=1e-12)
+        want = so.loglik_unit(x, G[b], H[b], form='chol')
+        assert abs(ll[b] - want) <= RTOL_LOGLIK * abs(want)

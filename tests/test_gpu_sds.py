@@ -255,3 +255,33 @@ def test_mid_size_batch_equals_single_chain_runs(gp):
         assert np.array_equal(Tc[:, 0], Ta[:, c])
         np.testing.assert_allclose(Hc[0], Ha[c], rtol=1e-12)
         assert np.abs(Fc[0] - Fa[c]).max() < 5e-2
+
+
+def test_sweep_survives_numerically_singular_states(gp, capfd):
+    """Chains whose K+S is numerically singular (noise ~1e-9, long length-scale) exercise the pyGPs jitter ladder
+    inside the sweep (sliceSample.py:196,205 via jitchol): the sweep must finish, report a status per chain, never
+    produce non-finite accepted states, and leave the well-conditioned chains of the same batch untouched."""
+    import os
+    import torch
+    from gpmc_b200 import ops
+    n = 256
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    H0 = np.array([[30.0, 3.0, 1e-9], [1.0, 10.0, 1.2], [25.0, 2.0, 1e-9], [5.0, 4.0, 2.5]])
+    F0 = np.zeros((4, n))
+
+    def run(rows):
+        F = torch.tensor(F0[rows].copy()).cuda(); H = torch.tensor(H0[rows].copy()).cuda()
+        nt, ll, st = ops.sds_sweep(x, y, F, H, scale, 600, seed=5, chain0=0, max_trips=12) if rows == [0, 1, 2, 3] else \
+            ops.sds_sweep(x, y, F, H, scale, 600, seed=5, chain0=rows[0], max_trips=12)
+        return F.cpu().numpy(), H.cpu().numpy(), nt.cpu().numpy(), st.cpu().numpy()
+    os.environ['GPMC_DEBUG'] = '1'
+    try:
+        F, H, nt, st = run([0, 1, 2, 3])
+    finally:
+        os.environ.pop('GPMC_DEBUG', None)
+    assert np.all(np.isfinite(F)) and np.all(np.isfinite(H)) and np.all((st == 0) | (st == 1)) and np.all(nt >= 1)
+    assert st[1] == 0 and st[3] == 0
+    # the healthy chains are not disturbed by their singular neighbours
+    F1, H1, n1, s1 = run([1])
+    assert np.array_equal(H1[0], H[1]) and n1[0] == nt[1]
