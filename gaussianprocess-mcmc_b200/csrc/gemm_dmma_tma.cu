@@ -21,7 +21,7 @@
 namespace gpmc {
 
 constexpr int TBM = 128, TBN = 64, TBK = 16;
-constexpr int TSTAGES = 3;
+constexpr int TSTAGES = 4;
 constexpr int TTHREADS = 256;
 constexpr int A_BYTES = TBM * TBK * 8;                 // 16 KiB
 constexpr int B_BYTES = TBN * TBK * 8;                 //  8 KiB

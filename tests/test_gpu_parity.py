@@ -287,3 +287,33 @@ def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
         np.testing.assert_allclose(L[b], ref, rtol=1e-10, atol=1e-12)
         want = so.loglik_unit(x, G[b], H[b], form='chol')
         assert abs(ll[b] - want) <= RTOL_LOGLIK * abs(want)
+
+
+@pytest.mark.parametrize('n,d', [(129, 2), (257, 3)])
+def test_iso_kernel_with_multidimensional_inputs(gp, so, n, d):
+    """covK.RBF on D > 1 inputs (one shared length-scale, P = 3): assembly and the fused unit."""
+    rs = np.random.RandomState(n)
+    x = rs.uniform(0, 20, size=(n, d))
+    H = np.array([[3.0, 6.0, 1.1], [0.8, 2.0, 0.4]])
+    A = gp.ops.cov_assemble(x, H).cpu().numpy()[:, :, :n]
+    G = rs.standard_normal((2, n))
+    ll, info = gp.ops.loglik_host(x, G, H)
+    assert np.all(info == 0)
+    for b in range(2):
+        np.testing.assert_allclose(A[b], so.cov_matrix(x, H[b]), rtol=2e-13, atol=1e-300)
+        ref = so.loglik_unit(x, G[b], H[b], form='chol')
+        assert abs(ll[b] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
+def test_odd_and_unaligned_sizes_through_the_fused_unit(gp, so):
+    """N that is odd / not a multiple of 16, 64 or 128: padded leading dimension, partial tiles and blocks."""
+    rs = np.random.RandomState(11)
+    for n in (3, 17, 127, 129, 191, 1001, 2047):
+        x = np.arange(n, dtype=np.float64).reshape(n, 1) * 0.9
+        H = np.array([[4.0, 5.0, 1.5], [1.2, 9.0, 0.7]])
+        G = rs.standard_normal((2, n))
+        ll, info = gp.ops.loglik_host(x, G, H)
+        assert np.all(info == 0)
+        for b in range(2):
+            ref = so.loglik_unit(x, G[b], H[b], form='chol')
+            assert abs(ll[b] - ref) <= RTOL_LOGLIK * abs(ref), (n, b)
