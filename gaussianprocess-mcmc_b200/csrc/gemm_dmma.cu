@@ -1,15 +1,19 @@
-// FP64 tensor-core (DMMA) tile kernel: every dense contraction of the hot path is an "NT" product
+// FP64 tensor-core (DMMA) tile kernel, cp.async-staged variants: every dense contraction of the hot path is an "NT"
+// product
 //     C[i][j]  (op)=  sum_k  A[i][k] * B[j][k]
 // of two row-major operands whose contraction index is contiguous in memory:
 //   * Cholesky block-column / trailing update   C -= L[i,:k] L[j,:k]^T          (kcGP.tools.jitchol -> dpotrf,
-//   * panel TRSM as a GEMM                      X  = A21 * (L11^-1)^T            sliceSample.py:196,205)
+//                                                                                 sliceSample.py:196,205)
 //   * triangular inverse U = L^-T, block column  Y  = U[:i,:i] L[i,:i]^T, then  U[:i,i] = -Y (L_ii^-1)^T
 //   * posterior covariance                      R  = S - S (U U^T) S (+1e-11 I)  (sliceSample.py:197-198,205 in the
 //                                                                                 algebraically reduced form)
 // sm_100a has no FP64 kind in tcgen05; FP64 tensor cores are reached with mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
-// CTA tile 128x128; operands are staged global -> shared with 16-byte cp.async in a 4-stage ring of K=16 chunks;
-// shared rows are padded to 20 doubles so the 8-byte fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct
-// bank pairs (ncu: 0 shared bank conflicts).  Rows beyond the matrix are zero-filled by cp.async's src-size operand.
+// The DEFAULT kernel is the TMA-staged one in gemm_dmma_tma.cu; the variants here (128x128 with 8 or 16 warps,
+// 128x64 with two CTAs per SM) stage operands with 16-byte cp.async into a ring of K=16 chunks whose rows are padded
+// to 20 doubles, so the 8-byte fragment loads of a half-warp (4 rows x 4 k) hit 16 distinct bank pairs (ncu: 0 shared
+// bank conflicts); rows beyond the matrix are zero-filled by cp.async's src-size operand.  They are kept for A/B
+// measurements (GPMC_GEMM_CFG / gpmc_set_tuning) and as the fallback when an operand cannot be described by a
+// tensor map.  launch_gemm() below dispatches.
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "../../include/gpmc.h"
