@@ -94,8 +94,8 @@ void set_gemm_config(int cfg);
 int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                  int B, cudaStream_t s);
 
-// trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21 by blocked substitution
-int launch_trsm_panel(BatchView A, int n, int j0, int B, cudaStream_t s);
+// trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
+int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
 
 // solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)
 //   a, b, zout are per-item vectors with row stride ldv (b, zout, loglik may be nullptr)

@@ -193,7 +193,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s);
             if (rc) return rc;
             if (j0 + NB < n) {
-                rc = launch_trsm_panel(A, n, j0, B, s);
+                rc = launch_trsm_panel(A, n, j0, Wj, strideW, B, s);
                 if (rc) return rc;
             }
         }

@@ -1,33 +1,32 @@
 // Panel triangular solve of the blocked Cholesky:  X L11^T = A21  (in place), i.e. the rows of L below a
 // factored 128x128 diagonal block -- the dtrsm inside LAPACK dpotrf (kcGP.tools.jitchol, sliceSample.py:196,205).
 //
-// It is a true substitution, not a multiplication by an explicit inverse: chol(R + 1e-11 I) at sliceSample.py:205
-// has condition ~1e11, and  A21 * inv(L11)  would lose cond(L11) * eps (measured: spurious "not positive definite"
-// pivots); substitution keeps the residual at eps * |X| |L11|.
+// Each 32-column sub-block is solved as  X0 = A W_d^T,  r = A - X0 L_d^T,  X = X0 + r W_d^T  (W_d = L_d^-1 from the
+// panel kernel): an inverse-multiply followed by ONE step of iterative refinement, all on FP64 DMMA.  The refinement
+// is what makes it safe: chol(R + 1e-11 I) at sliceSample.py:205 has condition ~1e11 and a plain  A21 * inv(L11)
+// (128-wide, what batched GPU Cholesky codes commonly do) loses cond(L11) * eps -- measured: spurious "not positive
+// definite" pivots on a golden fixture.  With the residual taken against the 32x32 block L_d itself the backward error
+// is back at eps * |X| |L_d| (the level of substitution) as long as cond(L_d) * eps << 1, and the dependent chain of a
+// substitution (128 steps of shuffle -> multiply -> fma per row) is gone.
 //
-// One CTA owns 64 rows of the panel (two CTAs per SM).  Each of its 8 warps keeps 8 rows x 128 columns as FP64 DMMA accumulator
-// fragments in registers for the whole kernel and, after the initial load of L11, never meets a block barrier.
-// The 128 columns are processed in four sub-blocks of 32:
-//   solve : substitution in the fragment layout itself -- column c of a row lives in one lane of the row's quad;
-//           the solved value is broadcast with a quad shuffle and each lane updates its own later columns with L
-//           entries read from shared memory (no explicit inverse anywhere)
-//   update: the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T  on DMMA; the solved sub-block is
-//           staged through the warp's own shared-memory rows to become A fragments (and goes out to global).
-// L11 is kept as its lower 32x32 blocks, staged with cp.async.
+// One CTA owns 128 rows of the panel; each of its 16 warps keeps 8 rows x 128 columns as DMMA accumulator fragments
+// in registers and never meets a block barrier after the initial load.  Per sub-block: three small DMMA products (the
+// triangular zero parts are skipped), then the later columns get  acc[:, later] -= X[:, sb] * L[later, sb]^T.
+// Fragment-layout changes (accumulator -> A operand) go through the warp's own shared-memory rows.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
 
-constexpr int TP_ROWS = 64;                   // rows per CTA; two CTAs per SM overlap each other's load/store phases
-constexpr int TP_B = 34;                      // stride of L blocks and of the staged sub-block: the substitution's
-                                              // L[j][c] reads (j = 2*fk + ..) fall in 4 distinct bank groups
-constexpr int TP_THREADS = 256;               // 8 warps x 8 rows, 2 CTAs per SM: the kernel is latency bound, warps hide it
+constexpr int TP_ROWS = 128;                  // rows per CTA
+constexpr int TP_B = 36;                      // stride of L / W blocks and of the staged sub-block (4 mod 16: conflict-free
+                                              // DMMA fragments)
+constexpr int TP_THREADS = 512;               // 16 warps x 8 rows
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
 constexpr int TP_NSB = NB / 32;               // 32-column sub-blocks of the panel
 constexpr int TP_NLB = TP_NSB * (TP_NSB + 1) / 2;   // lower 32x32 blocks of L11
 constexpr int TP_NC8 = NB / 8;                // 8-column fragments per row
-constexpr int TP_SMEM = (TP_ROWS * TP_B + TP_NLB * TP_LBLK + NB) * (int)sizeof(double);
+constexpr int TP_SMEM = (TP_ROWS * TP_B + (TP_NLB + TP_NSB) * TP_LBLK) * (int)sizeof(double);
 
 __device__ __forceinline__ int lblk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
 
@@ -38,13 +37,13 @@ __device__ __forceinline__ void dmma884_t(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(TP_THREADS, NB == 64 ? 3 : 2)
-trsm_panel_kernel(BatchView A, int n, int j0)
+__global__ void __launch_bounds__(TP_THREADS, 1)
+trsm_panel_kernel(BatchView A, int n, int j0, const double *__restrict__ W, long long strideW)
 {
     extern __shared__ __align__(16) double sm[];
     double *R = sm;                               // [128][36] the sub-block being solved
     double *Lb = sm + TP_ROWS * TP_B;             // 10 lower blocks of L11
-    double *dinv = Lb + TP_NLB * TP_LBLK;             // [128]
+    double *Wd = Lb + TP_NLB * TP_LBLK;           // the NB/32 diagonal 32x32 blocks of W = L11^-1
     const int b = blockIdx.y;
     if (A.count && b >= *A.count) return;
     const int m = batch_item(A, b);
@@ -66,6 +65,13 @@ trsm_panel_kernel(BatchView A, int n, int j0)
         const unsigned dst = (unsigned)__cvta_generic_to_shared(&Lb[blk * TP_LBLK + r * TP_B + c2]);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2));
     }
+    const double *Wb = W + (size_t)m * strideW;
+    for (int e = tid; e < TP_NSB * 32 * 16; e += TP_THREADS) {
+        const int d = e / (32 * 16), rem = e - d * 32 * 16;
+        const int r = rem / 16, c2 = (rem - r * 16) * 2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&Wd[d * TP_LBLK + r * TP_B + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wb + (size_t)(d * 32 + r) * NB + d * 32 + c2));
+    }
     asm volatile("cp.async.commit_group;\n" ::);
     // this warp's 8 rows as accumulator fragments: acc[cb8] = row warp*8 + fr, cols cb8*8 + 2fk, +1
     double acc[TP_NC8][2];
@@ -82,9 +88,10 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
-    if (tid < NB) {
-        const int bi = tid >> 5, r = tid & 31;
-        dinv[tid] = 1.0 / Lb[lblk_index(bi, bi) * TP_LBLK + r * TP_B + r];
+    // the strict upper triangle of the diagonal L blocks is garbage in global memory: the residual product needs zeros
+    for (int e = tid; e < TP_NSB * 32 * 32; e += TP_THREADS) {
+        const int d = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        if (c > r) Lb[lblk_index(d, d) * TP_LBLK + r * TP_B + c] = 0.0;
     }
     __syncthreads();
     // From here on every warp works on its own 16 rows only (L and dinv are read-only): no block barriers.
@@ -92,22 +99,55 @@ trsm_panel_kernel(BatchView A, int n, int j0)
 #pragma unroll
     for (int sb = 0; sb < TP_NSB; ++sb) {
         const double *Ld = Lb + lblk_index(sb, sb) * TP_LBLK;
-        // ---- solve the sub-block's 32 columns in fragment layout.  Column c lives in lane fk == (c%8)/2 of each
-        //      row's quad; the solved value is broadcast inside the quad and every lane updates its own later columns.
+        const double *Wq = Wd + sb * TP_LBLK;
+        // ---- X0 = A W_d^T : accumulator fragments -> A fragments through the warp's shared rows
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int CB = c >> 3, OW = (c & 7) >> 1, S = c & 1;
-            const double xs = __shfl_sync(0xffffffffu, acc[sb * 4 + CB][S] * dinv[sb * 32 + c], (lane & ~3) | OW);
-            if (fk == OW) acc[sb * 4 + CB][S] = xs;
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
+        __syncwarp();
+        double fa[8];
 #pragma unroll
-            for (int CB2 = CB; CB2 < 4; ++CB2) {
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ks * 4 + fk];
+        double x0[4][2];
 #pragma unroll
-                for (int S2 = 0; S2 < 2; ++S2) {
-                    const int j = CB2 * 8 + 2 * fk + S2;              // this lane's column
-                    if (CB2 > CB || j > c) acc[sb * 4 + CB2][S2] = fma(-xs, Ld[j * TP_B + c], acc[sb * 4 + CB2][S2]);
-                }
-            }
+        for (int q = 0; q < 4; ++q) {
+            x0[q][0] = x0[q][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks <= 2 * q + 1; ++ks)                       // W_d[c][k] = 0 for k > c
+                dmma884_t(x0[q][0], x0[q][1], fa[ks], Wq[(q * 8 + fr) * TP_B + ks * 4 + fk]);
         }
+        __syncwarp();
+        // ---- r = A - X0 L_d^T
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(x0[q][0], x0[q][1]);
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = -Rw[fr * TP_B + ks * 4 + fk];
+        double rr[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            rr[q][0] = acc[sb * 4 + q][0]; rr[q][1] = acc[sb * 4 + q][1];
+#pragma unroll
+            for (int ks = 0; ks <= 2 * q + 1; ++ks)                       // L_d[c][k] = 0 for k > c
+                dmma884_t(rr[q][0], rr[q][1], fa[ks], Ld[(q * 8 + fr) * TP_B + ks * 4 + fk]);
+        }
+        __syncwarp();
+        // ---- X = X0 + r W_d^T   (one step of iterative refinement)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(rr[q][0], rr[q][1]);
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ks * 4 + fk];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int ks = 0; ks <= 2 * q + 1; ++ks)
+                dmma884_t(x0[q][0], x0[q][1], fa[ks], Wq[(q * 8 + fr) * TP_B + ks * 4 + fk]);
+            acc[sb * 4 + q][0] = x0[q][0]; acc[sb * 4 + q][1] = x0[q][1];
+        }
+        __syncwarp();
         // ---- stage the solved columns (this warp's rows): final values -> global, and A fragments for the update
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -135,7 +175,7 @@ trsm_panel_kernel(BatchView A, int n, int j0)
     }
 }
 
-int launch_trsm_panel(BatchView A, int n, int j0, int B, cudaStream_t s)
+int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s)
 {
     const int rows = n - j0 - NB;
     if (B <= 0 || rows <= 0) return 0;
@@ -147,7 +187,7 @@ int launch_trsm_panel(BatchView A, int n, int j0, int B, cudaStream_t s)
     }
     dim3 grid((rows + TP_ROWS - 1) / TP_ROWS, B);
     prof_begin(KC_TRSM, s);
-    trsm_panel_kernel<<<grid, TP_THREADS, TP_SMEM, s>>>(A, n, j0);
+    trsm_panel_kernel<<<grid, TP_THREADS, TP_SMEM, s>>>(A, n, j0, W, strideW);
     prof_end(KC_TRSM, s);
     GPMC_LAUNCH_CHECK();
     return 0;
