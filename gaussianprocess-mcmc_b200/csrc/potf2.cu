@@ -10,8 +10,9 @@
 // rows of [A11; I] are updated alike).  Inner blocking is 32:
 //   * the 32x32 diagonal sub-block is factored by ONE WARP, one matrix row (and one identity row) per lane in
 //     registers, pivots and multipliers broadcast with warp shuffles -- no block barrier inside;
-//   * the sub-panel (rows of L below and rows of X above) is multiplied by the inverse of the sub-block and the
-//     trailing sub-blocks are updated with FP64 DMMA (mma.sync.m8n8k4) on fragments read from T.
+//   * the sub-panel rows of L below are solved against the sub-block (inverse-multiply + one refinement step, so the
+//     factor keeps the backward error of a substitution), the rows of X above are multiplied by its inverse, and the
+//     trailing sub-blocks are updated, all with FP64 DMMA (mma.sync.m8n8k4) on fragments read from T.
 // W = L11^-1 is written out dense so the panel TRSM below the block is a DMMA GEMM (gemm_dmma.cu).
 #include "common.cuh"
 #include "../../include/gpmc.h"
@@ -127,38 +128,61 @@ potf2_inv_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
         }
         __syncthreads();
         // ---------------------------------------------------------------- sub-panel (12 row blocks of 8)
-        //   rows below (L):  solve  x L_d^T = a  by substitution IN THE FRAGMENT LAYOUT: column c of a row lives in
-        //                    one lane of the row's quad, the solved value is broadcast with a quad shuffle and each
-        //                    lane updates its own later columns (backward stable: no explicit inverse on the factor)
+        //   rows below (L):  solve  x L_d^T = a  as inverse-multiply + one step of iterative refinement on DMMA
         //   rows above (X):  T[r][k0 + c] = sum_k T[r][k0 + k] * Lc[c][k]   -- this IS the inverse being built
         {
             const int nblk_below = (NB - k0 - PB) / 8, nblk_above = k0 / 8;
             for (int u = warp; u < nblk_below + nblk_above; u += POTF2_THREADS / 32) {
                 if (u < nblk_below) {
+                    // X0 = A Lc^T ; r = A - X0 L_d^T ; X = X0 + r Lc^T  (inverse-multiply + one refinement step: backward
+                    // error at the level of substitution, no dependent 32-step chain; see trsm_panel.cu)
                     const int r0 = k0 + PB + u * 8;
-                    double v[4][2];
+                    double fa[8], a0[4][2], x0[4][2], rr[4][2];
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) fa[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const double2 t2 = *reinterpret_cast<const double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]);
-                        v[q][0] = t2.x; v[q][1] = t2.y;
+                        a0[q][0] = t2.x; a0[q][1] = t2.y;
+                        x0[q][0] = x0[q][1] = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks <= 2 * q + 1; ++ks)
+                            dmma884_p(x0[q][0], x0[q][1], fa[ks], Lc[(q * 8 + fr) * PC + ks * 4 + fk]);
                     }
-#pragma unroll
-                    for (int c = 0; c < PB; ++c) {
-                        const int CB = c >> 3, OW = (c & 7) >> 1, S = c & 1;
-                        const double xs = __shfl_sync(0xffffffffu, v[CB][S] * dinv[k0 + c], (lane & ~3) | OW);
-                        if (fk == OW) v[CB][S] = xs;
-#pragma unroll
-                        for (int CB2 = CB; CB2 < 4; ++CB2) {
-#pragma unroll
-                            for (int S2 = 0; S2 < 2; ++S2) {
-                                const int j = CB2 * 8 + 2 * fk + S2;
-                                if (CB2 > CB || j > c) v[CB2][S2] = fma(-xs, T[(k0 + j) * PT + k0 + c], v[CB2][S2]);
-                            }
-                        }
-                    }
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]) = make_double2(v[q][0], v[q][1]);
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]) = make_double2(x0[q][0], x0[q][1]);
+                    __syncwarp();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) fa[ks] = -T[(r0 + fr) * PT + k0 + ks * 4 + fk];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        rr[q][0] = a0[q][0]; rr[q][1] = a0[q][1];
+#pragma unroll
+                        for (int ks = 0; ks <= 2 * q + 1; ++ks) {
+                            // L_d[c][k], k <= c: the diagonal sub-block's lower triangle (its strict upper part holds X_d)
+                            const int c = q * 8 + fr, k = ks * 4 + fk;
+                            dmma884_p(rr[q][0], rr[q][1], fa[ks], (k <= c) ? T[(k0 + c) * PT + k0 + k] : 0.0);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]) = make_double2(rr[q][0], rr[q][1]);
+                    __syncwarp();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) fa[ks] = T[(r0 + fr) * PT + k0 + ks * 4 + fk];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int ks = 0; ks <= 2 * q + 1; ++ks)
+                            dmma884_p(x0[q][0], x0[q][1], fa[ks], Lc[(q * 8 + fr) * PC + ks * 4 + fk]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<double2 *>(&T[(r0 + fr) * PT + k0 + q * 8 + 2 * fk]) = make_double2(x0[q][0], x0[q][1]);
                 } else {
                     const int r0 = (u - nblk_below) * 8;
                     double af[8];
