@@ -134,9 +134,10 @@ gemm_dmma_kernel(GemmArgs p)
 }
 
 bool gemm_tma_supported(const GemmArgs &a);
-int launch_gemm_tma(const GemmArgs &a, int B, int kclass, cudaStream_t s);
+int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cudaStream_t s);
 
-// 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged
+// 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged;
+// 4: TMA-staged with full/empty mbarrier pairs (no block barrier in the main loop)
 static int g_gemm_cfg = 3;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
@@ -169,12 +170,12 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
     static bool set0 = false, set1 = false, set2 = false, env_read = false;
     if (!env_read) {            // GPMC_GEMM_CFG=0..3 selects the tile-kernel variant (experiments / A-B tests)
         const char *e = getenv("GPMC_GEMM_CFG");
-        if (e && e[0] >= '0' && e[0] <= '3') g_gemm_cfg = e[0] - '0';
+        if (e && e[0] >= '0' && e[0] <= '4') g_gemm_cfg = e[0] - '0';
         env_read = true;
     }
-    if (g_gemm_cfg == 3 && gemm_tma_supported(a)) return launch_gemm_tma(a, B, kclass, s);
+    if (g_gemm_cfg >= 3 && gemm_tma_supported(a)) return launch_gemm_tma(a, B, kclass, g_gemm_cfg == 4, s);
     if (g_gemm_cfg == 0) return launch_variant(gemm_dmma_kernel<2, 4, 128, 4, 1>, a, B, 128, 256, gemm_smem_bytes(128, 4), kclass, s, set0);
-    if (g_gemm_cfg == 2 || g_gemm_cfg == 3) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
+    if (g_gemm_cfg >= 2) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
     return launch_variant(gemm_dmma_kernel<4, 4, 128, 4, 1>, a, B, 128, 512, gemm_smem_bytes(128, 4), kclass, s, set1);
 }
 

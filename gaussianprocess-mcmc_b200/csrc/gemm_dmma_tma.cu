@@ -26,7 +26,7 @@ constexpr int TTHREADS = 256;
 constexpr int A_BYTES = TBM * TBK * 8;                 // 16 KiB
 constexpr int B_BYTES = TBN * TBK * 8;                 //  8 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMA_SMEM = TSTAGES * STAGE_BYTES + 1024 + 64;   // + alignment slack + barriers
+constexpr int TMA_SMEM = TSTAGES * STAGE_BYTES + 1024 + 128;  // + alignment slack + barriers
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
@@ -50,6 +50,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
@@ -57,6 +61,11 @@ __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, 
                    "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// FREE_RUNNING = false: one __syncthreads per K chunk recycles the stages (all warps in lock step).
+// FREE_RUNNING = true : full/empty mbarrier pairs per stage -- every warp arrives on empty[s] when it has read stage s,
+//                       the producer thread refills a stage once its empty barrier completed, and no block barrier
+//                       is left in the main loop, so the eight warps drift apart instead of stalling together.
+template <bool FREE_RUNNING>
 __global__ void __launch_bounds__(TTHREADS, 2)
 gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB)
 {
@@ -64,6 +73,7 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024 B
     uint64_t *full = (uint64_t *)(smem + TSTAGES * STAGE_BYTES);
+    uint64_t *empty = full + TSTAGES;
     const int b = blockIdx.y;
     if (p.C.count && b >= *p.C.count) return;
     const int m = batch_item(p.C, b);
@@ -80,7 +90,7 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA));
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB));
-        for (int s = 0; s < TSTAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TTHREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
     }
     __syncthreads();
@@ -94,8 +104,8 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
         tma_load_3d(st, &tmA, &full[s], ak + chunk * TBK, arow, m);
         tma_load_3d(st + A_BYTES, &tmB, &full[s], bk + chunk * TBK, brow, m);
     };
-    if (tid == 0)
-        for (int s = 0; s < TSTAGES - 1 && s < nk; ++s) issue(s);
+    if (tid == 0)      // lock step: one stage stays free for the refill; free running: all stages start full
+        for (int s = 0; s < (FREE_RUNNING ? TSTAGES : TSTAGES - 1) && s < nk; ++s) issue(s);
 
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
@@ -114,10 +124,12 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     for (int kc = 0; kc < nk; ++kc) {
         const int s = kc % TSTAGES;
         mbar_wait(&full[s], (kc / TSTAGES) & 1);
-        __syncthreads();                                  // everyone is done with the stage refilled below
-        if (tid == 0 && kc + TSTAGES - 1 < nk) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            issue(kc + TSTAGES - 1);
+        if (!FREE_RUNNING) {
+            __syncthreads();                              // everyone is done with the stage refilled below
+            if (tid == 0 && kc + TSTAGES - 1 < nk) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                issue(kc + TSTAGES - 1);
+            }
         }
         const unsigned char *sa = smem + s * STAGE_BYTES + (wm * FM * 8 + frow) * 128;
         const unsigned char *sb = smem + s * STAGE_BYTES + A_BYTES + (wn * FN * 8 + frow) * 128;
@@ -128,6 +140,18 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
             for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double *>(sa + i * 8 * 128 + foff[ks]);
 #pragma unroll
             for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double *>(sb + j * 8 * 128 + foff[ks]);
+            if (FREE_RUNNING && ks == 3) {
+                // the fragments of this stage are in registers: release it, and let the producer refill the stage
+                // that every warp released one chunk ago
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (tid == 0 && kc >= 1 && kc + TSTAGES - 1 < nk) {
+                    const int prev = kc - 1;
+                    mbar_wait(&empty[prev % TSTAGES], (prev / TSTAGES) & 1);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    issue(kc + TSTAGES - 1);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -180,13 +204,14 @@ bool gemm_tma_supported(const GemmArgs &a)
            a.A.ld >= TBK && a.B.ld >= TBK;
 }
 
-int launch_gemm_tma(const GemmArgs &a, int B, int kclass, cudaStream_t s)
+int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cudaStream_t s)
 {
     int rc = get_encoder();
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+        GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+        GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -198,7 +223,8 @@ int launch_gemm_tma(const GemmArgs &a, int B, int kclass, cudaStream_t s)
     const int tiles = a.lower_only ? (TBM / TBN) * tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
     dim3 grid(tiles, B);
     prof_begin(kclass, s);
-    gemm_dmma_tma_kernel<<<grid, TTHREADS, TMA_SMEM, s>>>(a, tmA, tmB);
+    if (free_running) gemm_dmma_tma_kernel<true><<<grid, TTHREADS, TMA_SMEM, s>>>(a, tmA, tmB);
+    else gemm_dmma_tma_kernel<false><<<grid, TTHREADS, TMA_SMEM, s>>>(a, tmA, tmB);
     prof_end(kclass, s);
     GPMC_LAUNCH_CHECK();
     return 0;
