@@ -138,7 +138,7 @@ int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cud
 
 // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged;
 // 4: TMA-staged with full/empty mbarrier pairs (no block barrier in the main loop)
-static int g_gemm_cfg = 3;
+static int g_gemm_cfg = 4;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 template <typename K>

@@ -263,7 +263,7 @@ def test_loglik_large_single_matrix(gp, so):
     assert abs(ll[0] - ref) <= RTOL_LOGLIK * abs(ref)
 
 
-@pytest.mark.parametrize('cfg', [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
     """The DMMA tile kernel exists in four variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
     per SM, TMA-staged 128x64); all must give the same factor."""
@@ -279,7 +279,7 @@ def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
         G = np.random.RandomState(cfg).standard_normal((2, n))
         ll, _ = gp.ops.loglik_host(x, G, H)
     finally:
-        gp.ops.set_tuning(0, 3)
+        gp.ops.set_tuning(0, 4)
     assert np.all(info.cpu().numpy() == 0)
     L = A.cpu().numpy()[:, :, :n]
     for b in range(2):
