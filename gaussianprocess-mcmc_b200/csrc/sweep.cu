@@ -36,8 +36,11 @@ struct SweepBuffers {
 
 static char *carve(char *&p, size_t bytes) { char *r = p; p += align_up(bytes, 256); return r; }
 
-static void layout(SweepBuffers &w, char *p, int n, int P, int cap)
+// Carve the wave's buffers out of `base` (nullptr: only measure).  Returns the number of bytes used, so the size query
+// and the real layout can never disagree.
+static size_t layout(SweepBuffers &w, char *base, int n, int P, int cap)
 {
+    char *p = base;
     w.n = n; w.ld = ld_for(n); w.ldv = w.ld; w.P = P; w.nt = (n + NB - 1) / NB; w.cap = cap;
     const size_t mat = (size_t)n * w.ld * 8;
     w.buf1 = (double *)carve(p, mat * cap);
@@ -53,22 +56,13 @@ static void layout(SweepBuffers &w, char *p, int n, int P, int cap)
     int **ints[] = {&w.done, &w.ntrips, &w.map, &w.info1, &w.info2, &w.bad, &w.fmap};
     for (int **v : ints) *v = (int *)carve(p, (size_t)4 * cap);
     w.count = (int *)carve(p, 256);
+    return (size_t)(p - base);
 }
 
 static size_t sweep_bytes(int n, int P, int cap)
 {
-    // the carve arithmetic of layout(), replayed without a base pointer
-    const int ld = ld_for(n), nt = (n + NB - 1) / NB;
-    const size_t mat = (size_t)n * ld * 8;
-    size_t tot = 0;
-    auto add = [&](size_t b) { tot += align_up(b, 256); };
-    add(mat * cap); add(mat * cap); add((size_t)nt * NB * NB * 8 * cap); add((size_t)NB * NB * 8 * cap);
-    for (int i = 0; i < 8; ++i) add((size_t)ld * 8 * cap);
-    for (int i = 0; i < 5; ++i) add((size_t)P * 8 * cap);
-    for (int i = 0; i < 10; ++i) add((size_t)8 * cap);
-    for (int i = 0; i < 7; ++i) add((size_t)4 * cap);
-    add(256);
-    return tot + 256;
+    SweepBuffers w;
+    return layout(w, nullptr, n, P, cap) + 256;
 }
 
 // S_ii and diag(K+S) on the host (sliceSample.py:185-190 expression order), used only to size the ladder's jitter
