@@ -47,6 +47,14 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(n, B, world):
+    """`config` of the JSON line: identical for the CUDA arm and the reference arm."""
+    return {'workload': 'BASELINE config 5 (8xB200 chain-parallel: N=4096, 8192 chains sharded by GPU): %d chains '
+                        'per GPU, one log-lik eval per chain per step, SE+noise kernel on a unit-spaced 1-D grid '
+                        '(IH45-shaped)' % B,
+            'n': n, 'chains_per_gpu': B, 'evals_per_step': world * B, 'kernel': 'SE iso + noise'}
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU every 200 ms while the timed region runs."""
@@ -136,9 +144,11 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 5 shape: N=%d log-lik evals, one chain after another on the host '
-                               '(the reference has no multi-chain mode, framework.py:68-75)' % args.n,
-                   'evals_per_step': sample, 'form': 'sliceSample.py:136-137,183-190,196,147 (dense inv)'},
+        'config': dict(workload_config(args.n, args.chains_per_gpu, max(1, args.gpus)),
+                       reference_sample='each timed step is a bounded sample of that workload: %d evals, one chain after '
+                                        'another on the host (the reference has no multi-chain mode, framework.py:68-75), '
+                                        'in the form the reference writes: sliceSample.py:136-137,183-190,196,147 '
+                                        '(dense inv)' % sample),
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d steps x %d evals at N=%d, numpy/scipy OpenBLAS on %d threads' % (args.steps, sample, args.n, cores)},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -318,12 +328,9 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 5 (8xB200 chain-parallel: N=4096, 8192 chains sharded by GPU): %d chains '
-                               'per GPU, one log-lik eval per chain per step, SE+noise kernel on a unit-spaced 1-D grid '
-                               '(IH45-shaped)' % B,
-                   'n': n, 'chains_per_gpu': B, 'evals_per_step': world * B, 'kernel': 'SE iso + noise',
-                   'l2': 'per-step working set %d matrices x %.0f MiB >> 126 MB L2 (no flush needed)' % (B, n * n * 8 / 2 ** 20),
-                   'collective': 'one all_gather of loglik per step' if world > 1 else 'none (single rank)'},
+        'config': dict(workload_config(n, B, world),
+                       l2='per-step working set %d matrices x %.0f MiB >> 126 MB L2 (no flush needed)' % (B, n * n * 8 / 2 ** 20),
+                       collective='one all_gather of loglik per step' if world > 1 else 'none (single rank)'),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(sum(v[1] for v in prof.values())),
         'roofline': roofline, 'cpu_baseline': cpu,
     }
