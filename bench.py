@@ -49,9 +49,9 @@ def parse():
 
 def workload_config(n, B, world):
     """`config` of the JSON line: identical for the CUDA arm and the reference arm."""
-    return {'workload': 'BASELINE config 5 (8xB200 chain-parallel: N=4096, 8192 chains sharded by GPU): %d chains '
+    return {'workload': 'BASELINE config 5 (8xB200 chain-parallel: N=4096, 8192 chains sharded by GPU): N=%d, %d chains '
                         'per GPU, one log-lik eval per chain per step, SE+noise kernel on a unit-spaced 1-D grid '
-                        '(IH45-shaped)' % B,
+                        '(IH45-shaped)' % (n, B),
             'n': n, 'chains_per_gpu': B, 'evals_per_step': world * B, 'kernel': 'SE iso + noise'}
 
 
