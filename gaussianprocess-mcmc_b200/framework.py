@@ -74,3 +74,55 @@ class singleRun(Framework):
         histF, histHyp = self.runSimulMCMC(iterMCMC)                 # framework.py:164
         self.output(histHyp=histHyp.T, histF=histF, out_dir=out_dir)  # framework.py:165
         return histF, histHyp
+
+
+class crossValid(Framework):
+    """Cross-validated runs: mirrors ``framework.py:177-248`` -- for every gap and fold hold out ``gap`` points out of
+    every ``gap + window``, run the sampler on the rest, predict the held-out points from every 10th sample of the last
+    tenth of the chain with ``inf_mcmc`` and score them with the truncated-Gaussian predictive likelihood."""
+
+    def __init__(self, data, window, gapArray):
+        super(crossValid, self).__init__(data, window, gapArray)
+        self.windowSize = window
+        self.gapArray = gapArray
+
+    def getFoldData(self, fold, gap, window):
+        """``framework.py:124-147`` (integer division made explicit for Python 3)."""
+        test_id = []
+        for i in range(self.x.shape[0] // (gap + window)):
+            test_id = np.append(test_id, fold + np.arange(gap) + (gap + window) * i)
+        test_id = np.asarray(test_id)
+        test_id = test_id[test_id < self.x.shape[0]].astype('int')
+        train_id = np.delete(np.arange(self.x.shape[0]), test_id)
+        return self.x[train_id, :], self.y[train_id, 0], self.x[test_id, :], self.y[test_id, 0], test_id
+
+    def execute(self, updOpt='mcmcSml', iterMCMC=1000, out_dir='./output'):
+        import types
+        from .kcGP import covK, likK
+        from .kcMCMC import sliceSample
+        assert updOpt == 'mcmcSml', 'only the MCMC path is part of this package'
+        originalX, originalY = self.x[:], self.y[:]
+        results = {}
+        zero_mean = types.SimpleNamespace(getMean=lambda a: np.zeros((a.shape[0], 1)))
+        for gap in self.gapArray:
+            gapLLK = []
+            for fold in range(gap + self.windowSize):
+                self.x, self.y = originalX, originalY
+                trX, trY, valX, valY, _ = self.getFoldData(fold, gap, window=self.windowSize)
+                self.x, self.y = trX, trY.reshape(-1, 1)
+                foldF, foldHyp = self.runSimulMCMC(iterMCMC)
+                upper, lower = 100. - np.mean(self.y), 0. - np.mean(self.y)
+                foldLLK = []
+                for i in range(iterMCMC * 9 // 10 - 1, iterMCMC, 10):                  # framework.py:223
+                    ll, sf, sn = foldHyp[0, i], foldHyp[1, i], foldHyp[2, i]
+                    trunclik = likK.TruncatedGauss2(upper=upper, lower=lower, log_sigma=np.log(sn))
+                    model = types.SimpleNamespace(x=self.x, y=self.y, xs=valX, meanfunc=zero_mean,
+                                                  covfunc=covK.RBF(np.log(ll), np.log(sf)), likfunc=trunclik)
+                    ys, _, _, fs2 = sliceSample.inf_mcmc(foldF[:, i].reshape(-1, 1), model)
+                    trunclik.upper, trunclik.lower = 100., 0.                           # framework.py:241-242
+                    foldLLK.append(trunclik.evaluate(y=ys, mu=valY.reshape(-1, 1), s2=fs2) / ys.shape[0])
+                gapLLK.append(float(np.mean(foldLLK)))
+            self.x, self.y = originalX, originalY
+            self.output(gap, foldHyp.T, foldF, gapLLK, out_dir=out_dir)                 # framework.py:248 (last fold's chain)
+            results[gap] = gapLLK
+        return results

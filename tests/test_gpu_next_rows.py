@@ -145,3 +145,17 @@ def test_framework_loop_matches_oracle_on_the_global_stream(gp, tmp_path):
     assert rows[0] == 'll,sf2,sn' and len(rows) == iters + 1
     head = open(os.path.join(str(tmp_path), 'fGap2.csv')).readline().strip().split(',')
     assert head == [str(i) for i in range(1, iters + 1)] + ['x', 'y']
+
+
+def test_cross_validation_driver(gp, tmp_path):
+    """crossValid.execute (framework.py:195-248): folds, sampler, inf_mcmc prediction, predictive score, CSV files."""
+    n = 60
+    x, y = gp.synthetic.ih45_series(n)
+    cv = gp.framework.crossValid(np.column_stack([y, x]), window=4, gapArray=[1])
+    trX, trY, vaX, vaY, tid = cv.getFoldData(2, 1, 4)
+    assert list(tid) == list(range(2, n, 5)) and trX.shape[0] == n - len(tid) and np.array_equal(vaY, y[tid])
+    np.random.seed(3)
+    res = cv.execute(iterMCMC=20, out_dir=str(tmp_path))
+    assert list(res) == [1] and len(res[1]) == 5 and np.all(np.isfinite(res[1]))
+    assert os.path.isfile(os.path.join(str(tmp_path), 'hypGap1.csv')) and os.path.isfile(os.path.join(str(tmp_path), 'llkGap1.csv'))
+    assert cv.x.shape[0] == n                                           # data restored
