@@ -122,7 +122,7 @@ class crossValid(Framework):
                     trunclik.upper, trunclik.lower = 100., 0.                           # framework.py:241-242
                     foldLLK.append(trunclik.evaluate(y=ys, mu=valY.reshape(-1, 1), s2=fs2) / ys.shape[0])
                 gapLLK.append(float(np.mean(foldLLK)))
+            self.output(gap, foldHyp.T, foldF, gapLLK, out_dir=out_dir)                 # framework.py:248 (last fold's chain and data)
             self.x, self.y = originalX, originalY
-            self.output(gap, foldHyp.T, foldF, gapLLK, out_dir=out_dir)                 # framework.py:248 (last fold's chain)
             results[gap] = gapLLK
         return results
