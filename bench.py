@@ -313,7 +313,7 @@ def run_b200(args):
         roofline['assemble']['hbm_peak_gbs'] = 6650.0
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # the CPU arm is reported at N=1 only
         v_inv, dt_inv, vals = cpu_unit_evals_per_s(n, args.cpu_sample, 'inv')
         v_chol, dt_chol, vals_c = cpu_unit_evals_per_s(n, args.cpu_sample, 'trsv')
         got = ll.cpu().numpy()[:args.cpu_sample]
