@@ -383,6 +383,7 @@ int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_ou
 int gpmc_set_tuning(int key, int value)
 {
     if (key == 0) { set_gemm_config(value); return 0; }
+    if (key == 1) { set_potf2_mode(value); return 0; }
     return GPMC_EINVAL;
 }
 

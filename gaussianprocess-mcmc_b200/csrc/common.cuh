@@ -93,6 +93,11 @@ void set_gemm_config(int cfg);
 // potf2.cu : factor the NB x NB diagonal block at (j0, j0) in place, write its inverse to W
 int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                  int B, cudaStream_t s);
+// potf2_lite.cu : same factor, but only the inverses of the four 32x32 diagonal sub-blocks are written to W (all that
+// launch_trsm_panel reads); 2 CTAs per SM.  Not for callers that go on to inverse_sequence.
+int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
+                      int B, cudaStream_t s);
+void set_potf2_mode(int mode);     // 0 auto (lite when the full inverse is not needed and B > #SMs), 1 always full, 2 lite whenever legal
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);

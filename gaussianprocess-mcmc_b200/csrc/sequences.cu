@@ -170,9 +170,14 @@ static int potrf_window_for(int n, int B)
     return n >= 8192 ? 1024 : 512;
 }
 
+static int g_potf2_mode = 0;
+void set_potf2_mode(int mode) { g_potf2_mode = mode; }
+
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper_flag, cudaStream_t s)
 {
+    // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
+    const bool lite = (w_step == 0) && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > 148));
     const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
@@ -190,7 +195,8 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 int rc = launch_gemm(g, B, KC_GEMM, s);
                 if (rc) return rc;
             }
-            int rc = launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s);
+            int rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s)
+                          : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s);
             if (rc) return rc;
             if (j0 + NB < n) {
                 rc = launch_trsm_panel(A, n, j0, Wj, strideW, B, s);

@@ -172,7 +172,9 @@ int gpmc_cov_cross(const double *x_dev, int N, const double *z_dev, int M, int D
 int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ldmu, int N, int B, const double *sn_dev,
                     double lower, double upper, double *out_dev, void *stream);
 
-/* Kernel tuning knobs for experiments (key 0: DMMA tile kernel variant, 0 = 8 warps 64x32, 1 = 16 warps 32x32). */
+/* Kernel tuning knobs for experiments.
+ * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default).
+ * key 1: panel factor kernel (0 auto, 1 always the full-inverse kernel, 2 the diagonal-inverse kernel whenever legal). */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
