@@ -173,11 +173,22 @@ static int potrf_window_for(int n, int B)
 static int g_potf2_mode = 0;
 void set_potf2_mode(int mode) { g_potf2_mode = mode; }
 
+static int sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper_flag, cudaStream_t s)
 {
     // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
-    const bool lite = (w_step == 0) && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > 148));
+    const bool lite = (w_step == 0) && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > sm_count()));
     const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
