@@ -84,6 +84,8 @@ struct GemmArgs {
     int lower_only;        // enumerate only tiles with tile-row >= tile-col (square output, SYRK use)
     int k_follow_row;      // A (and B) are upper triangular in (row, k): start k at the tile's first A row
     int epi;               // Epilogue
+    int skip_upper;        // C's strict upper triangle (global row < global col) is never read by the caller: warps whose
+                           // whole sub-tile lies there may skip their contraction and leave C untouched
     const double *svec;    // EPI_R: per-item diagonal of S, [N]
     long long stride_s;
 };

@@ -121,6 +121,26 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
         for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // diagonal tiles of a symmetric update: a warp whose 32x32 sub-tile is strictly above the diagonal has nothing to
+    // contribute (6 of the 16 sub-tiles of a 128x128 diagonal block) -- it only keeps the stage hand-shake going and
+    // leaves its DMMA issue slots to the other resident warps
+    const bool skip = p.skip_upper && (p.cr0 + tm * TBM + (wm + 1) * FM * 8 - 1 < p.cc0 + tn * TBN + wn * FN * 8);
+    if (FREE_RUNNING && skip) {
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % TSTAGES;
+            mbar_wait(&full[s], (kc / TSTAGES) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (tid == 0 && kc >= 1 && kc + TSTAGES - 1 < nk) {
+                const int prev = kc - 1;
+                mbar_wait(&empty[prev % TSTAGES], (prev / TSTAGES) & 1);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                issue(kc + TSTAGES - 1);
+            }
+        }
+        return;
+    }
+
     for (int kc = 0; kc < nk; ++kc) {
         const int s = kc % TSTAGES;
         mbar_wait(&full[s], (kc / TSTAGES) & 1);

@@ -203,6 +203,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
                 g.ar0 = j0; g.br0 = j0; g.k0 = w0; g.bk0 = w0; g.klen = j0 - w0;
                 g.epi = EPI_SUB;
+                g.skip_upper = 1;                       // potf2 reads the lower triangle of the diagonal block only
                 int rc = launch_gemm(g, B, KC_GEMM, s);
                 if (rc) return rc;
             }
@@ -221,6 +222,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             g.ar0 = w1; g.br0 = w1; g.k0 = w0; g.bk0 = w0; g.klen = w1 - w0;
             g.lower_only = 1;
             g.epi = EPI_SUB;
+            g.skip_upper = 1;
             int rc = launch_gemm(g, B, KC_GEMM, s);
             if (rc) return rc;
         }
@@ -273,6 +275,7 @@ int r_sequence(BatchView Rm, BatchView U, int n, int B, const double *svec, long
     g.ar0 = 0; g.br0 = 0; g.k0 = 0; g.bk0 = 0; g.klen = n;
     g.lower_only = 1; g.k_follow_row = 1;
     g.epi = EPI_R; g.svec = svec; g.stride_s = stride_s;
+    g.skip_upper = 1;                                   // only chol(R + 1e-11 I) reads R, and only its lower triangle
     return launch_gemm(g, B, KC_SYRK_R, s);
 }
 
