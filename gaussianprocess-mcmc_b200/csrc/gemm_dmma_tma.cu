@@ -16,6 +16,7 @@
 #include "../../include/gpmc.h"
 
 #include <cuda.h>
+#include <type_traits>
 #include <cudaTypedefs.h>
 
 namespace gpmc {
@@ -125,6 +126,7 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     // contribute (6 of the 16 sub-tiles of a 128x128 diagonal block) -- it only keeps the stage hand-shake going and
     // leaves its DMMA issue slots to the other resident warps
     const bool skip = p.skip_upper && (p.cr0 + tm * TBM + (wm + 1) * FM * 8 - 1 < p.cc0 + tn * TBN + wn * FN * 8);
+    const bool on_diag = p.skip_upper && (p.cr0 + tm * TBM + wm * FM * 8 == p.cc0 + tn * TBN + wn * FN * 8);
     if (FREE_RUNNING && skip) {
         for (int kc = 0; kc < nk; ++kc) {
             const int s = kc % TSTAGES;
@@ -141,43 +143,52 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
         return;
     }
 
-    for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % TSTAGES;
-        mbar_wait(&full[s], (kc / TSTAGES) & 1);
-        if (!FREE_RUNNING) {
-            __syncthreads();                              // everyone is done with the stage refilled below
-            if (tid == 0 && kc + TSTAGES - 1 < nk) {
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                issue(kc + TSTAGES - 1);
-            }
-        }
-        const unsigned char *sa = smem + s * STAGE_BYTES + (wm * FM * 8 + frow) * 128;
-        const unsigned char *sb = smem + s * STAGE_BYTES + A_BYTES + (wn * FN * 8 + frow) * 128;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            double af[FM], bf[FN];
-#pragma unroll
-            for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double *>(sa + i * 8 * 128 + foff[ks]);
-#pragma unroll
-            for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double *>(sb + j * 8 * 128 + foff[ks]);
-            if (FREE_RUNNING && ks == 3) {
-                // the fragments of this stage are in registers: release it, and let the producer refill the stage
-                // that every warp released one chunk ago
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-                if (tid == 0 && kc >= 1 && kc + TSTAGES - 1 < nk) {
-                    const int prev = kc - 1;
-                    mbar_wait(&empty[prev % TSTAGES], (prev / TSTAGES) & 1);
+    // the K loop, in two compiled shapes: every 8x8 block of the warp's sub-tile, or (sub-tile ON the diagonal of a
+    // skip_upper update) only the blocks with j <= i -- chosen once per warp, outside the loop
+    auto main_loop = [&](auto diag_tag) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % TSTAGES;
+            mbar_wait(&full[s], (kc / TSTAGES) & 1);
+            if (!FREE_RUNNING) {
+                __syncthreads();                              // everyone is done with the stage refilled below
+                if (tid == 0 && kc + TSTAGES - 1 < nk) {
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     issue(kc + TSTAGES - 1);
                 }
             }
+            const unsigned char *sa = smem + s * STAGE_BYTES + (wm * FM * 8 + frow) * 128;
+            const unsigned char *sb = smem + s * STAGE_BYTES + A_BYTES + (wn * FN * 8 + frow) * 128;
 #pragma unroll
-            for (int i = 0; i < FM; ++i)
+            for (int ks = 0; ks < 4; ++ks) {
+                double af[FM], bf[FN];
 #pragma unroll
-                for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double *>(sa + i * 8 * 128 + foff[ks]);
+#pragma unroll
+                for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double *>(sb + j * 8 * 128 + foff[ks]);
+                if (FREE_RUNNING && ks == 3) {
+                    // the fragments of this stage are in registers: release it, and let the producer refill the stage
+                    // that every warp released one chunk ago
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                    if (tid == 0 && kc >= 1 && kc + TSTAGES - 1 < nk) {
+                        const int prev = kc - 1;
+                        mbar_wait(&empty[prev % TSTAGES], (prev / TSTAGES) & 1);
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        issue(kc + TSTAGES - 1);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j)
+                        if (!DIAG || j <= i) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
         }
-    }
+    };
+    // lock step keeps every warp on one path (block barriers inside the loop)
+    if (FREE_RUNNING && on_diag) main_loop(std::true_type{});
+    else main_loop(std::false_type{});
     gemm_epilogue<FM, FN, TBM, TBN>(p, m, tm, tn, wm, wn, frow, fk, rows_valid, cols_valid, acc);
 }
 
