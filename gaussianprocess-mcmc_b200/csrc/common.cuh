@@ -99,6 +99,8 @@ int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *
 // launch_trsm_panel reads); 2 CTAs per SM.  Not for callers that go on to inverse_sequence.
 int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                       int B, cudaStream_t s);
+void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on
+void set_potrf_window(int w);      // override the window of the windowed schedule (multiple of NB; 0 = default)
 void set_potf2_mode(int mode);     // 0 auto (lite when the full inverse is not needed and B > #SMs), 1 always full, 2 lite whenever legal
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)

@@ -80,6 +80,7 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     const int m = batch_item(p.C, b);
     int tm, tn;
     gemm_tile_decode<TBM, TBN>(p, blockIdx.x, tm, tn);
+    if (p.skip_upper && p.cr0 + tm * TBM + TBM - 1 < p.cc0 + tn * TBN) return;     // whole tile above the diagonal
     const int rows_valid = min(TBM, p.rows - tm * TBM);
     const int cols_valid = min(TBN, p.cols - tn * TBN);
     int koff = 0;

@@ -163,10 +163,14 @@ int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows,
 // matrices: B * N/128 < 1024, e.g. the single N=16384 matrix of BASELINE config 4) the columns are grouped in WINDOWS:
 // left-looking inside a window (contraction limited to the window), then ONE right-looking trailing update
 // A22 -= L21 L21^T with thousands of tiles and K = window -- the classic DMMA trailing update.
+static int g_window_override = 0;
+void set_potrf_window(int w) { g_window_override = (w > 0 && w % NB == 0) ? w : 0; }
+
 static int potrf_window_for(int n, int B)
 {
     const int nt = (n + 127) / 128;                 // 128-row tiles of a block column
     if ((long long)B * nt >= 1024) return 0;
+    if (g_window_override) return g_window_override;
     return n >= 8192 ? 1024 : 512;
 }
 
@@ -184,6 +188,39 @@ static int sm_count()
     return sms;
 }
 
+// Look-ahead.  With few matrices in flight the panel kernels (one CTA per matrix) leave most of the chip idle, so the
+// sequence is spread over up to three streams:
+//   * P (high priority): potf2 + panel solve of block column j,
+//   * Q: the in-window update of block column j+1, split in a LONG part (contraction over everything left of column j:
+//     independent of what P is doing, runs concurrently with it) and a SHORT part (K = the 128 columns P just finished),
+//   * G (the caller's stream): the right-looking trailing update after a window, split in the part that touches the
+//     NEXT window's columns (everything in that window waits for it) and the rest, which overlaps the next window.
+// Dependencies are expressed with events only; the caller's stream joins everything before potrf_sequence returns.
+struct LookAhead {
+    cudaStream_t panel = nullptr, inwin = nullptr;
+    cudaEvent_t ev_q = nullptr, ev_p = nullptr, ev_a = nullptr;
+    bool ok = false;
+};
+static LookAhead *lookahead_ctx()
+{
+    static LookAhead la;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        int lo = 0, hi = 0;
+        bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&la.panel, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&la.inwin, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&la.ev_q, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&la.ev_p, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&la.ev_a, cudaEventDisableTiming) == cudaSuccess;
+        la.ok = ok;
+    }
+    return la.ok ? &la : nullptr;
+}
+static int g_lookahead_mode = 0;       // 0 auto (B <= #SMs / 2), 1 off, 2 on
+void set_lookahead_mode(int mode) { g_lookahead_mode = mode; }
+
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper_flag, cudaStream_t s)
 {
@@ -192,38 +229,74 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
+    LookAhead *la = nullptr;
+    if (n > 2 * NB && (g_lookahead_mode == 2 || (g_lookahead_mode == 0 && 2 * B <= sm_count()))) la = lookahead_ctx();
+    // streams: trailing updates / in-window updates / panel kernels
+    const cudaStream_t sG = s;
+    const cudaStream_t sQ = la ? (window > 0 ? la->inwin : s) : s;
+    const cudaStream_t sP = la ? la->panel : s;
+
+    auto update = [&](int j0, int width, int k_begin, int k_end, cudaStream_t st) -> int {
+        GemmArgs g{};
+        g.C = A; g.A = self; g.B = self;
+        g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
+        g.ar0 = j0; g.br0 = j0; g.k0 = k_begin; g.bk0 = k_begin; g.klen = k_end - k_begin;
+        g.epi = EPI_SUB;
+        g.skip_upper = 1;                               // potf2 reads the lower triangle of the diagonal block only
+        return launch_gemm(g, B, KC_GEMM, st);
+    };
+
     for (int w0 = 0; w0 < n; w0 += wlen) {
         const int w1 = std::min(n, w0 + wlen);
-        for (int j0 = w0; j0 < w1; j0 += NB) {
-            const int width = std::min(NB, n - j0);
-            double *Wj = W + (size_t)(j0 / NB) * w_step;
-            if (j0 > w0) {
+        if (la && sQ != sG) {                           // this window's columns are final on G up to here
+            GPMC_CUDA_CHECK(cudaEventRecord(la->ev_a, sG));
+            GPMC_CUDA_CHECK(cudaStreamWaitEvent(sQ, la->ev_a, 0));
+            if (w0 > 0 && w1 < n) {
+                // the rest of the previous window's trailing update: columns right of this window (overlaps it)
                 GemmArgs g{};
                 g.C = A; g.A = self; g.B = self;
-                g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
-                g.ar0 = j0; g.br0 = j0; g.k0 = w0; g.bk0 = w0; g.klen = j0 - w0;
+                g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = n - w1;
+                g.ar0 = w1; g.br0 = w1; g.k0 = w0 - wlen; g.bk0 = w0 - wlen; g.klen = wlen;
+                g.lower_only = 1;
                 g.epi = EPI_SUB;
-                g.skip_upper = 1;                       // potf2 reads the lower triangle of the diagonal block only
-                int rc = launch_gemm(g, B, KC_GEMM, s);
-                if (rc) return rc;
-            }
-            int rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s)
-                          : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, s);
-            if (rc) return rc;
-            if (j0 + NB < n) {
-                rc = launch_trsm_panel(A, n, j0, Wj, strideW, B, s);
+                g.skip_upper = 1;
+                int rc = launch_gemm(g, B, KC_GEMM, sG);
                 if (rc) return rc;
             }
         }
+        for (int j0 = w0; j0 < w1; j0 += NB) {
+            const int width = std::min(NB, n - j0);
+            double *Wj = W + (size_t)(j0 / NB) * w_step;
+            int rc;
+            if (!la) {
+                if (j0 > w0 && (rc = update(j0, width, w0, j0, s))) return rc;
+            } else {
+                if (j0 - NB > w0 && (rc = update(j0, width, w0, j0 - NB, sQ))) return rc;         // long part
+                if (j0 > w0) {
+                    GPMC_CUDA_CHECK(cudaStreamWaitEvent(sQ, la->ev_p, 0));                        // column j-1 solved
+                    if ((rc = update(j0, width, j0 - NB, j0, sQ))) return rc;                     // short part
+                }
+                GPMC_CUDA_CHECK(cudaEventRecord(la->ev_q, sQ));
+                GPMC_CUDA_CHECK(cudaStreamWaitEvent(sP, la->ev_q, 0));
+            }
+            rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
+                      : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP);
+            if (rc) return rc;
+            if (j0 + NB < n && (rc = launch_trsm_panel(A, n, j0, Wj, strideW, B, sP))) return rc;
+            if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
+        }
+        if (la) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sG, la->ev_p, 0));                            // join
         if (w1 < n) {
+            const bool split = la && sQ != sG;
+            const int w2 = std::min(n, w1 + wlen);
             GemmArgs g{};
             g.C = A; g.A = self; g.B = self;
-            g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = n - w1;
+            g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = split ? w2 - w1 : n - w1;
             g.ar0 = w1; g.br0 = w1; g.k0 = w0; g.bk0 = w0; g.klen = w1 - w0;
-            g.lower_only = 1;
-            g.epi = EPI_SUB;
+            g.lower_only = split ? 0 : 1;               // split: the next window's columns first (rectangular, the tiles
+            g.epi = EPI_SUB;                            // above the diagonal exit at once), the rest at the top of the loop
             g.skip_upper = 1;
-            int rc = launch_gemm(g, B, KC_GEMM, s);
+            int rc = launch_gemm(g, B, KC_GEMM, sG);
             if (rc) return rc;
         }
     }

@@ -295,6 +295,30 @@ def test_loglik_large_single_matrix(gp, so):
     assert abs(ll[0] - ref) <= RTOL_LOGLIK * abs(ref)
 
 
+@pytest.mark.parametrize('n,B', [(1000, 3), (2500, 1), (3000, 2), (600, 40)])
+def test_lookahead_schedule_equals_sequential_schedule(gp, so, n, B):
+    """The blocked Cholesky overlaps panel kernels and update GEMMs on side streams when few matrices are in flight
+    (sequences.cu).  Forced on and forced off must agree (same kernels, the update's contraction is only split in two),
+    match the oracle, and be reproducible run to run (a missing dependency would show as run-to-run differences)."""
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(B, n)
+    out = {}
+    try:
+        for mode in (1, 2):
+            gp.ops.set_tuning(2, mode)
+            runs = [gp.ops.loglik_host(x, G, H) for _ in range(4 if mode == 2 else 1)]
+            for ll, info in runs:
+                assert np.all(info == 0)
+                assert np.array_equal(ll, runs[0][0])
+            out[mode] = runs[0][0]
+    finally:
+        gp.ops.set_tuning(2, 0)
+    np.testing.assert_allclose(out[2], out[1], rtol=1e-12)
+    for b in range(min(B, 2)):
+        ref = so.loglik_unit(x, G[b], H[b], form='trsv')
+        assert abs(out[2][b] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
     """The DMMA tile kernel exists in four variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
