@@ -85,7 +85,7 @@ static LoglikLayout loglik_layout(int N, int B)
 {
     LoglikLayout l;
     l.ld = ld_for(N);
-    l.mat_elems = (size_t)N * l.ld;
+    l.mat_elems = (size_t)(N + 1) * l.ld;            // + the border row that carries g through the factorisation
     l.per_item_bytes = l.mat_elems * sizeof(double) + (size_t)NB * NB * sizeof(double);
     l.fixed_bytes = align_up((size_t)B * sizeof(double), 256)      // jitter
                     + align_up((size_t)B * sizeof(int), 256)       // map
@@ -254,7 +254,8 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
         BatchView A{mats, (long long)l.mat_elems, l.ld, nullptr, nullptr};
         int rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A, nb, s);
         if (rc) return rc;
-        rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s);
+        if ((rc = border_set(A, N, g_w, N, nb, s))) return rc;
+        rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s, 1);
         if (rc) return rc;
         if (jitter_policy == GPMC_JITTER_PYGPS) {
             std::vector<int> info(nb);
@@ -283,7 +284,8 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                     BatchView Am{mats, (long long)l.mat_elems, l.ld, map_dev, nullptr};
                     rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, jit_dev, Am, nf, s);
                     if (rc) return rc;
-                    rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s);
+                    if ((rc = border_set(Am, N, g_w, N, nf, s))) return rc;
+                    rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s, 1);
                     if (rc) return rc;
                     GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
                     GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -296,7 +298,8 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                 GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
             }
         }
-        rc = launch_solve_reduce(A, N, g_w, nullptr, N, (nb < 32 && (N & 1) == 0) ? zscratch : nullptr, loglik_dev + s0, info_w, nb, s);
+        // z = L^-1 g sits in the border row except for the last column block: finish it, then quad form + log det
+        rc = border_finish(A, N, loglik_dev + s0, info_w, nb, s);
         if (rc) return rc;
     }
     return 0;

@@ -86,6 +86,8 @@ struct GemmArgs {
     int epi;               // Epilogue
     int skip_upper;        // C's strict upper triangle (global row < global col) is never read by the caller: warps whose
                            // whole sub-tile lies there may skip their contraction and leave C untouched
+    int border_row;        // > 0 (EPI_SUB, skip_upper, cr0 == cc0, A == C buffers): global row of a right-hand side carried as a
+                           // ROW below the matrix; it receives the same update, C[border_row, cols] -= A[border_row, k] B[cols, k]^T
     const double *svec;    // EPI_R: per-item diagonal of S, [N]
     long long stride_s;
 };
@@ -110,6 +112,8 @@ int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long str
 //   a, b, zout are per-item vectors with row stride ldv (b, zout, loglik may be nullptr)
 int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, int ldv, double *zout,
                         double *loglik, const int *info, int B, cudaStream_t s);
+// loglik[m] = -(0.5 z.z + sum_i log L_ii + 0.5 n log 2pi) from a finished z (row stride ldv per item)
+int launch_quad_logdet(BatchView L, int n, const double *z, int ldv, double *loglik, const int *info, int B, cudaStream_t s);
 // trmv.cu : out = T x (+ add) for a triangular row-major T;  upper=0: lower triangle, upper=1: upper triangle.
 //   mode 0: out = T x + add            (f' = C eta + m, sliceSample.py:140)
 //   mode 1: out = add - svec * (T x)   (m = g - S (K+S)^-1 g with T = L^-T, x = L^-1 g; sliceSample.py:204)

@@ -173,7 +173,17 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
         if (e && e[0] >= '0' && e[0] <= '4') g_gemm_cfg = e[0] - '0';
         env_read = true;
     }
-    if (g_gemm_cfg >= 3 && gemm_tma_supported(a)) return launch_gemm_tma(a, B, kclass, g_gemm_cfg == 4, s);
+    const bool border_fusable = a.border_row == 0 || (a.skip_upper && a.epi == EPI_SUB && a.cr0 == a.cc0 && a.A.base == a.C.base);
+    if (g_gemm_cfg == 4 && gemm_tma_supported(a) && border_fusable) return launch_gemm_tma(a, B, kclass, true, s);   // border row fused in-kernel
+    if (a.border_row > 0) {
+        // the other variants have no border duty: take the row along as one more output row (it follows the matrix)
+        if (a.cr0 + a.rows != a.border_row || a.ar0 != a.cr0) { set_error("gemm: border row %d is not adjacent to the output rows", a.border_row); return GPMC_EINVAL; }
+        GemmArgs b = a;
+        b.rows += 1;
+        b.border_row = 0;
+        return launch_gemm(b, B, kclass, s);
+    }
+    if (g_gemm_cfg == 3 && gemm_tma_supported(a)) return launch_gemm_tma(a, B, kclass, false, s);
     if (g_gemm_cfg == 0) return launch_variant(gemm_dmma_kernel<2, 4, 128, 4, 1>, a, B, 128, 256, gemm_smem_bytes(128, 4), kclass, s, set0);
     if (g_gemm_cfg >= 2) return launch_variant(gemm_dmma_kernel<4, 2, 64, 3, 2>, a, B, 64, 256, gemm_smem_bytes(64, 3), kclass, s, set2);
     return launch_variant(gemm_dmma_kernel<4, 4, 128, 4, 1>, a, B, 128, 512, gemm_smem_bytes(128, 4), kclass, s, set1);

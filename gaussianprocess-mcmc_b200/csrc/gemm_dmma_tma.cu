@@ -126,12 +126,45 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     // diagonal tiles of a symmetric update: a warp whose 32x32 sub-tile is strictly above the diagonal has nothing to
     // contribute (6 of the 16 sub-tiles of a 128x128 diagonal block) -- it only keeps the stage hand-shake going and
     // leaves its DMMA issue slots to the other resident warps
-    const bool skip = p.skip_upper && (p.cr0 + tm * TBM + (wm + 1) * FM * 8 - 1 < p.cc0 + tn * TBN + wn * FN * 8);
+    // ... and so has a warp whose rows all lie beyond the output (ragged last row tile, e.g. a single border row)
+    const bool skip = (wm * FM * 8 >= rows_valid) ||
+                      (p.skip_upper && (p.cr0 + tm * TBM + (wm + 1) * FM * 8 - 1 < p.cc0 + tn * TBN + wn * FN * 8));
     const bool on_diag = p.skip_upper && (p.cr0 + tm * TBM + wm * FM * 8 == p.cc0 + tn * TBN + wn * FN * 8);
     if (FREE_RUNNING && skip) {
+        // Border duty: in a tile on the diagonal the warp (wm, wn) = (0, 1) is always one of the skippers.  It carries
+        // the right-hand side stored as row p.border_row through the same update for the tile's 64 columns:
+        // one real row in the 8-row A fragment (read straight from global memory, one chunk ahead), B fragments
+        // from the staged tile -- 8 DMMAs per k step instead of none.
+        const bool duty = p.border_row > 0 && wm == 0 && wn == 1 && (p.cr0 + tm * TBM == p.cc0 + (tn * TBN) / TBM * TBM);
+        const double *zrow = p.A.base + (size_t)m * p.A.stride + (size_t)p.border_row * p.A.ld + ak;
+        const int kq = (fk >> 1) * 8 + (fk & 1);        // this lane's k inside a chunk at step ks: kq + 2 ks (the permuted order)
+        double bacc[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j][0] = bacc[j][1] = 0.0;
+        double zn[4] = {0.0, 0.0, 0.0, 0.0};
+        auto zload = [&](int chunk) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int k = chunk * TBK + kq + 2 * ks;
+                zn[ks] = (frow == 0 && k < klen) ? zrow[k] : 0.0;
+            }
+        };
+        if (duty && nk > 0) zload(0);
         for (int kc = 0; kc < nk; ++kc) {
             const int s = kc % TSTAGES;
+            double zc[4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) zc[ks] = zn[ks];
+            if (duty && kc + 1 < nk) zload(kc + 1);
             mbar_wait(&full[s], (kc / TSTAGES) & 1);
+            if (duty) {
+                const unsigned char *sb = smem + s * STAGE_BYTES + A_BYTES + frow * 128;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dmma884(bacc[j][0], bacc[j][1], zc[ks], *reinterpret_cast<const double *>(sb + j * 8 * 128 + foff[ks]));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (tid == 0 && kc >= 1 && kc + TSTAGES - 1 < nk) {
@@ -139,6 +172,19 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
                 mbar_wait(&empty[prev % TSTAGES], (prev / TSTAGES) & 1);
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 issue(kc + TSTAGES - 1);
+            }
+        }
+        if (duty && frow == 0) {
+            double *crow = p.C.base + (size_t)m * p.C.stride + (size_t)p.border_row * p.C.ld + p.cc0 + tn * TBN;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cl = j * 8 + fk * 2;
+                if (cl >= cols_valid) continue;
+                if (cl + 1 < cols_valid) {
+                    double2 c = *reinterpret_cast<const double2 *>(crow + cl);
+                    c.x -= bacc[j][0]; c.y -= bacc[j][1];
+                    *reinterpret_cast<double2 *>(crow + cl) = c;
+                } else crow[cl] -= bacc[j][0];
             }
         }
         return;

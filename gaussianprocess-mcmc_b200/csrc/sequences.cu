@@ -222,8 +222,10 @@ static int g_lookahead_mode = 0;       // 0 auto (B <= #SMs / 2), 1 off, 2 on
 void set_lookahead_mode(int mode) { g_lookahead_mode = mode; }
 
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
-                   int zero_upper_flag, cudaStream_t s)
+                   int zero_upper_flag, cudaStream_t s, int border_rows)
 {
+    if (border_rows < 0 || border_rows > 1) { set_error("potrf_sequence: at most one border row"); return GPMC_EINVAL; }
+    const int nr = n + border_rows;                     // rows that take part in the panel solves
     // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
     const bool lite = (w_step == 0) && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > sm_count()));
     const int window = potrf_window_for(n, B);
@@ -240,6 +242,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
         GemmArgs g{};
         g.C = A; g.A = self; g.B = self;
         g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
+        g.border_row = border_rows ? n : 0;
         g.ar0 = j0; g.br0 = j0; g.k0 = k_begin; g.bk0 = k_begin; g.klen = k_end - k_begin;
         g.epi = EPI_SUB;
         g.skip_upper = 1;                               // potf2 reads the lower triangle of the diagonal block only
@@ -256,6 +259,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 GemmArgs g{};
                 g.C = A; g.A = self; g.B = self;
                 g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = n - w1;
+                g.border_row = border_rows ? n : 0;
                 g.ar0 = w1; g.br0 = w1; g.k0 = w0 - wlen; g.bk0 = w0 - wlen; g.klen = wlen;
                 g.lower_only = 1;
                 g.epi = EPI_SUB;
@@ -282,7 +286,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
                       : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP);
             if (rc) return rc;
-            if (j0 + NB < n && (rc = launch_trsm_panel(A, n, j0, Wj, strideW, B, sP))) return rc;
+            if (j0 + NB < n && (rc = launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP))) return rc;
             if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
         }
         if (la) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sG, la->ev_p, 0));                            // join
@@ -292,6 +296,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             GemmArgs g{};
             g.C = A; g.A = self; g.B = self;
             g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = split ? w2 - w1 : n - w1;
+            g.border_row = border_rows ? n : 0;
             g.ar0 = w1; g.br0 = w1; g.k0 = w0; g.bk0 = w0; g.klen = w1 - w0;
             g.lower_only = split ? 0 : 1;               // split: the next window's columns first (rectangular, the tiles
             g.epi = EPI_SUB;                            // above the diagonal exit at once), the rest at the top of the loop
@@ -302,6 +307,37 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     }
     if (zero_upper_flag) return zero_upper(A, n, B, s);
     return 0;
+}
+
+// ------------------------------------------------------------------ border row (right-hand side carried as row n)
+__global__ void border_set_kernel(BatchView A, int n, const double *__restrict__ rhs, int ldv)
+{
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.ld) A.base[(size_t)m * A.stride + (size_t)n * A.ld + i] = (i < n) ? rhs[(size_t)m * ldv + i] : 0.0;
+}
+
+int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    border_set_kernel<<<dim3((A.ld + 255) / 256, B), 256, 0, s>>>(A, n, rhs, ldv);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    if (A.stride > 0x7fffffffLL) { set_error("border_finish: item stride %lld does not fit the vector stride", A.stride); return GPMC_EINVAL; }
+    const int j0 = (n - 1) / NB * NB;                   // last block column: its part of the row is updated, not solved
+    const int nv = n - j0;
+    double *row = A.base + (size_t)n * A.ld;            // item m's border row = row + m * stride
+    BatchView D{A.base + (size_t)j0 * A.ld + j0, A.stride, A.ld, A.map, A.count};
+    int rc = launch_solve_reduce(D, nv, row + j0, nullptr, (int)A.stride, row + j0, nullptr, info, B, s);
+    if (rc || !loglik) return rc;
+    return launch_quad_logdet(A, n, row, (int)A.stride, loglik, info, B, s);
 }
 
 // U = L^-T, built block column by block column in the upper triangle of the same buffer:

@@ -7,8 +7,19 @@ namespace gpmc {
 // Left-looking blocked Cholesky of every item of A (lower, in place).  The inverse of diagonal block j is
 // written to W + item*strideW + j*w_step (w_step = 0: one scratch block per item, overwritten every step;
 // w_step = NB*NB: all blocks kept, as inverse_sequence needs them).
+//
+// border_rows > 0: the buffer holds that many extra rows below the matrix (rows n .. n+border_rows-1, right-hand sides
+// stored as ROWS).  They ride through the update GEMMs and panel solves like any other row below the diagonal, so on
+// return row n holds (L^-1 rhs)^T for every column block but the last (the bordered-matrix form of forward
+// substitution: chol([[A, g], [g^T, c]]) has (L^-1 g)^T as its last row); border_finish() completes the last block.
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
-                   int zero_upper, cudaStream_t s);
+                   int zero_upper, cudaStream_t s, int border_rows = 0);
+
+// Write rhs[item] (length n, row stride ldv) into border row n of every item (zero padded up to ld).
+int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream_t s);
+// Finish z = L^-1 rhs in border row n (solve against the last diagonal block) and, when loglik != nullptr,
+// loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2 pi)  (sliceSample.py:122,147); NaN for items with info != 0.
+int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s);
 
 // In place L (lower) -> U = L^-T (upper triangle incl. diagonal blocks; the strict lower block part keeps L).
 // Needs the saved diagonal-block inverses of potrf_sequence (w_step = NB*NB).

@@ -202,6 +202,16 @@ quad_logdet_kernel(BatchView L, int n, const double *__restrict__ z, int ldv, do
     }
 }
 
+int launch_quad_logdet(BatchView L, int n, const double *z, int ldv, double *loglik, const int *info, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    prof_begin(KC_SOLVE, s);
+    quad_logdet_kernel<<<B, 256, 0, s>>>(L, n, z, ldv, loglik, info);
+    prof_end(KC_SOLVE, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, int ldv, double *zout,
                         double *loglik, const int *info, int B, cudaStream_t s)
 {

@@ -21,12 +21,13 @@ namespace gpmc {
 constexpr int TP_ROWS = 128;                  // rows per CTA
 constexpr int TP_B = 36;                      // stride of L / W blocks and of the staged sub-block (4 mod 16: conflict-free
                                               // DMMA fragments)
-constexpr int TP_THREADS = 512;               // 16 warps x 8 rows
+constexpr int TP_THREADS = 544;               // 16 warps x 8 rows + one warp for a border row that follows a full last CTA
+constexpr int TP_SROWS = TP_ROWS + 8;         // staging rows
 constexpr int TP_LBLK = 32 * TP_B;            // doubles per 32x32 L block
 constexpr int TP_NSB = NB / 32;               // 32-column sub-blocks of the panel
 constexpr int TP_NLB = TP_NSB * (TP_NSB + 1) / 2;   // lower 32x32 blocks of L11
 constexpr int TP_NC8 = NB / 8;                // 8-column fragments per row
-constexpr int TP_SMEM = (TP_ROWS * TP_B + (TP_NLB + TP_NSB) * TP_LBLK) * (int)sizeof(double);
+constexpr int TP_SMEM = (TP_SROWS * TP_B + (TP_NLB + TP_NSB) * TP_LBLK) * (int)sizeof(double);
 
 __device__ __forceinline__ int lblk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
 
@@ -38,11 +39,11 @@ __device__ __forceinline__ void dmma884_t(double &c0, double &c1, double a, doub
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1)
-trsm_panel_kernel(BatchView A, int n, int j0, const double *__restrict__ W, long long strideW)
+trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW)
 {
     extern __shared__ __align__(16) double sm[];
     double *R = sm;                               // [128][36] the sub-block being solved
-    double *Lb = sm + TP_ROWS * TP_B;             // 10 lower blocks of L11
+    double *Lb = sm + TP_SROWS * TP_B;            // 10 lower blocks of L11
     double *Wd = Lb + TP_NLB * TP_LBLK;           // the NB/32 diagonal 32x32 blocks of W = L11^-1
     const int b = blockIdx.y;
     if (A.count && b >= *A.count) return;
@@ -50,7 +51,8 @@ trsm_panel_kernel(BatchView A, int n, int j0, const double *__restrict__ W, long
     double *Ab = A.base + (size_t)m * A.stride;
     const int ld = A.ld;
     const int row0 = j0 + NB + blockIdx.x * TP_ROWS;
-    const int rows_valid = min(TP_ROWS, n - row0);
+    // n_rows counts the border rows too; the last CTA takes every row that is left (at most 128 + 1 border row)
+    const int rows_valid = (blockIdx.x == gridDim.x - 1) ? min(TP_SROWS, n_rows - row0) : TP_ROWS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
 
@@ -94,7 +96,8 @@ trsm_panel_kernel(BatchView A, int n, int j0, const double *__restrict__ W, long
         if (c > r) Lb[lblk_index(d, d) * TP_LBLK + r * TP_B + c] = 0.0;
     }
     __syncthreads();
-    // From here on every warp works on its own 16 rows only (L and dinv are read-only): no block barriers.
+    // From here on every warp works on its own 8 rows only (L and W are read-only): no block barriers.
+    if (warp * 8 >= rows_valid) return;           // ragged last CTA (e.g. only a border row): nothing to solve
     double *Rw = R + warp * 8 * TP_B;             // this warp's staging rows
 #pragma unroll
     for (int sb = 0; sb < TP_NSB; ++sb) {
@@ -175,10 +178,13 @@ trsm_panel_kernel(BatchView A, int n, int j0, const double *__restrict__ W, long
     }
 }
 
-int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s)
+// n_rows = matrix order + border rows (0 or 1); a border row that follows a full last CTA is taken by that CTA's 17th warp
+int launch_trsm_panel(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s)
 {
-    const int rows = n - j0 - NB;
+    const int n = n_rows;
+    int rows = n_rows - j0 - NB;
     if (B <= 0 || rows <= 0) return 0;
+    if (rows > 1 && rows % TP_ROWS == 1) rows -= 1;         // 128 k + 1: the extra row rides in the last CTA
     if ((A.ld & 1) || (j0 & 1)) { set_error("trsm_panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
     static bool attr_set = false;
     if (!attr_set) {
