@@ -327,6 +327,23 @@ int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream
     return 0;
 }
 
+__global__ void border_get_kernel(BatchView A, int n, double *__restrict__ z, int ldv, const int *__restrict__ info)
+{
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[(size_t)m * ldv + i] = (info && info[m] != 0) ? nan("") : A.base[(size_t)m * A.stride + (size_t)n * A.ld + i];
+}
+
+int border_get(BatchView A, int n, double *z, int ldv, const int *info, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    border_get_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(A, n, z, ldv, info);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
 int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s)
 {
     if (B <= 0) return 0;

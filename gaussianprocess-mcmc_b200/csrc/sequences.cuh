@@ -20,6 +20,8 @@ int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream
 // Finish z = L^-1 rhs in border row n (solve against the last diagonal block) and, when loglik != nullptr,
 // loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2 pi)  (sliceSample.py:122,147); NaN for items with info != 0.
 int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s);
+// Copy the border row out: z[item] (row stride ldv) = row n of the item (NaN for items with info != 0).
+int border_get(BatchView A, int n, double *z, int ldv, const int *info, int B, cudaStream_t s);
 
 // In place L (lower) -> U = L^-T (upper triangle incl. diagonal blocks; the strict lower block part keeps L).
 // Needs the saved diagonal-block inverses of potrf_sequence (w_step = NB*NB).

@@ -27,6 +27,7 @@ namespace gpmc {
 
 struct SweepBuffers {
     int n, ld, ldv, P, nt, cap;                  // cap = chains per wave
+    long long mat;                               // doubles per matrix slot: n rows + the border row that carries g
     double *buf1, *buf2, *Wsave, *Wtmp;
     double *Fin, *Fout, *g, *svec, *fprop, *z, *m, *eta;          // [cap, ldv]
     double *theta, *hyp_min, *hyp_max, *hyp_in, *hyp_out;         // [cap, P]
@@ -42,7 +43,8 @@ static size_t layout(SweepBuffers &w, char *base, int n, int P, int cap)
 {
     char *p = base;
     w.n = n; w.ld = ld_for(n); w.ldv = w.ld; w.P = P; w.nt = (n + NB - 1) / NB; w.cap = cap;
-    const size_t mat = (size_t)n * w.ld * 8;
+    w.mat = (long long)(n + 1) * w.ld;
+    const size_t mat = (size_t)w.mat * 8;
     w.buf1 = (double *)carve(p, mat * cap);
     w.buf2 = (double *)carve(p, mat * cap);
     w.Wsave = (double *)carve(p, (size_t)w.nt * NB * NB * 8 * cap);
@@ -123,7 +125,7 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     cudaStream_t s = c.s;
     const int na = (int)active.size();
     if (na == 0) return 0;
-    const long long mat = (long long)w.n * w.ld;
+    const long long mat = w.mat;
     BatchView A1{w.buf1, mat, w.ld, w.map, w.count};
     BatchView A2{w.buf2, mat, w.ld, w.map, w.count};
     const long long strideW = (long long)w.nt * NB * NB;
@@ -131,7 +133,9 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     // ---- K+S and its Cholesky factor (jitchol, :196)
     if ((rc = fill_int_mapped(w.info1, 0, w.map, w.count, na, s))) return rc;
     if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A1, na, s))) return rc;
-    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s))) return rc;
+    // g rides through the factorisation as a border row: z = L^-1 g comes out of the update GEMMs and panel solves
+    if ((rc = border_set(A1, w.n, w.g, w.ldv, na, s))) return rc;
+    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
     if (c.jitter_policy == GPMC_JITTER_PYGPS) {
         std::vector<int> failed, info;
         if ((rc = failed_items(c, w.info1, active, failed, info))) return rc;
@@ -156,7 +160,8 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
                 BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
                 if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
                 if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, w.jit, F1, nf, s))) return rc;
-                if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s))) return rc;
+                if ((rc = border_set(F1, w.n, w.g, w.ldv, nf, s))) return rc;
+                if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
                 std::vector<int> still, info2;
                 if ((rc = failed_items(c, w.info1, todo, still, info2))) return rc;
                 for (int id : still) jit[id] *= 10.0;
@@ -168,7 +173,8 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
         }
     }
     // ---- z = L^-1 g and the log marginal (:147)
-    if ((rc = launch_solve_reduce(A1, w.n, w.g, nullptr, w.ldv, w.z, w.G, w.info1, na, s))) return rc;
+    if ((rc = border_finish(A1, w.n, w.G, w.info1, na, s))) return rc;
+    if ((rc = border_get(A1, w.n, w.z, w.ldv, w.info1, na, s))) return rc;
     // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
     if ((rc = inverse_sequence(A1, w.n, na, w.Wsave, strideW, s))) return rc;
     if ((rc = launch_trmv(A1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, na, s))) return rc;
@@ -354,7 +360,7 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
         active.resize(nb);
         for (int i = 0; i < nb; ++i) active[i] = i;
         if ((rc = aux_eval(ctx, active))) return rc;
-        BatchView C2{w.buf2, (long long)N * w.ld, w.ld, w.map, w.count};
+        BatchView C2{w.buf2, w.mat, w.ld, w.map, w.count};
         if ((rc = launch_solve_reduce(C2, N, w.Fin, w.m, w.ldv, w.eta, nullptr, w.info2, nb, s))) return rc;     // eta, :108
         if ((rc = launch_sds_threshold(st, nb, s))) return rc;
         GPMC_CUDA_CHECK(cudaMemcpyAsync(w.loglik_out, w.G, (size_t)nb * 8, cudaMemcpyDeviceToDevice, s));
