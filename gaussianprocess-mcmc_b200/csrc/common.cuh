@@ -86,6 +86,8 @@ struct GemmArgs {
     int epi;               // Epilogue
     int skip_upper;        // C's strict upper triangle (global row < global col) is never read by the caller: warps whose
                            // whole sub-tile lies there may skip their contraction and leave C untouched
+    int in_place;          // C overlaps A's contraction range (C = -(C W^T) in inverse_sequence): ONE CTA must own all columns
+                           // of its rows and finish reading them before it writes -> 128-column tile kernel, cols <= 128
     int border_row;        // > 0 (EPI_SUB, skip_upper, cr0 == cc0, A == C buffers): global row of a right-hand side carried as a
                            // ROW below the matrix; it receives the same update, C[border_row, cols] -= A[border_row, k] B[cols, k]^T
     const double *svec;    // EPI_R: per-item diagonal of S, [N]

@@ -382,6 +382,7 @@ int inverse_sequence(BatchView A, int n, int B, const double *W, long long strid
             h.cr0 = 0; h.cc0 = i0; h.rows = i0; h.cols = width;
             h.ar0 = 0; h.br0 = 0; h.k0 = i0; h.bk0 = 0; h.klen = (width + 15) & ~15;   // stays inside ld (pads are zero)
             h.epi = EPI_NEGSET;
+            h.in_place = 1;                             // Y is overwritten by -(Y W_i^T)
             rc = launch_gemm(h, B, KC_INV, s);
             if (rc) return rc;
         }
