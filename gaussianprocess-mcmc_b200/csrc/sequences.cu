@@ -322,7 +322,9 @@ __global__ void border_set_kernel(BatchView A, int n, const double *__restrict__
 int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream_t s)
 {
     if (B <= 0) return 0;
+    prof_begin(KC_VEC, s);
     border_set_kernel<<<dim3((A.ld + 255) / 256, B), 256, 0, s>>>(A, n, rhs, ldv);
+    prof_end(KC_VEC, s);
     GPMC_LAUNCH_CHECK();
     return 0;
 }
@@ -339,7 +341,9 @@ __global__ void border_get_kernel(BatchView A, int n, double *__restrict__ z, in
 int border_get(BatchView A, int n, double *z, int ldv, const int *info, int B, cudaStream_t s)
 {
     if (B <= 0) return 0;
+    prof_begin(KC_VEC, s);
     border_get_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(A, n, z, ldv, info);
+    prof_end(KC_VEC, s);
     GPMC_LAUNCH_CHECK();
     return 0;
 }

@@ -31,6 +31,8 @@ constexpr int TP_SMEM = (TP_SROWS * TP_B + (TP_NLB + TP_NSB) * TP_LBLK) * (int)s
 
 __device__ __forceinline__ int lblk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
 
+__device__ __forceinline__ int stage_rot(int row) { return ((0x0310 >> ((row & 3) * 4)) & 0xf) * 4; }
+
 __device__ __forceinline__ void dmma884_t(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -99,6 +101,10 @@ trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W,
     // From here on every warp works on its own 8 rows only (L and W are read-only): no block barriers.
     if (warp * 8 >= rows_valid) return;           // ragged last CTA (e.g. only a border row): nothing to solve
     double *Rw = R + warp * 8 * TP_B;             // this warp's staging rows
+    // staging rows are rotated by {0, 4, 12, 0}[row & 3] columns: with stride 36 alone the 16-byte fragment stores of rows
+    // fr and fr+1 share bank groups (2-way conflict, ncu: 10 M conflicts per launch); with the rotation both the 16-byte
+    // stores (quarter-warp: rows fr, fr+1) and the 8-byte fragment loads (half-warp: rows fr..fr+3) are conflict free
+    const int rot = stage_rot(fr);
 #pragma unroll
     for (int sb = 0; sb < TP_NSB; ++sb) {
         const double *Ld = Lb + lblk_index(sb, sb) * TP_LBLK;
@@ -106,11 +112,11 @@ trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W,
         // ---- X0 = A W_d^T : accumulator fragments -> A fragments through the warp's shared rows
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + ((q * 8 + 2 * fk + rot) & 31)]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
         __syncwarp();
         double fa[8];
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ks * 4 + fk];
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ((ks * 4 + fk + rot) & 31)];
         double x0[4][2];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -123,10 +129,10 @@ trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W,
         // ---- r = A - X0 L_d^T
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(x0[q][0], x0[q][1]);
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + ((q * 8 + 2 * fk + rot) & 31)]) = make_double2(x0[q][0], x0[q][1]);
         __syncwarp();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) fa[ks] = -Rw[fr * TP_B + ks * 4 + fk];
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = -Rw[fr * TP_B + ((ks * 4 + fk + rot) & 31)];
         double rr[4][2];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -139,10 +145,10 @@ trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W,
         // ---- X = X0 + r W_d^T   (one step of iterative refinement)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(rr[q][0], rr[q][1]);
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + ((q * 8 + 2 * fk + rot) & 31)]) = make_double2(rr[q][0], rr[q][1]);
         __syncwarp();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ks * 4 + fk];
+        for (int ks = 0; ks < 8; ++ks) fa[ks] = Rw[fr * TP_B + ((ks * 4 + fk + rot) & 31)];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -154,19 +160,19 @@ trsm_panel_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W,
         // ---- stage the solved columns (this warp's rows): final values -> global, and A fragments for the update
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + q * 8 + 2 * fk]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
+            *reinterpret_cast<double2 *>(&Rw[fr * TP_B + ((q * 8 + 2 * fk + rot) & 31)]) = make_double2(acc[sb * 4 + q][0], acc[sb * 4 + q][1]);
         __syncwarp();
         for (int e = lane; e < 8 * 16; e += 32) {
             const int r = e >> 4, c2 = (e & 15) * 2;
             if (warp * 8 + r < rows_valid)
                 *reinterpret_cast<double2 *>(Ab + (size_t)(row0 + warp * 8 + r) * ld + j0 + sb * 32 + c2) =
-                    *reinterpret_cast<const double2 *>(&Rw[r * TP_B + c2]);
+                    *reinterpret_cast<const double2 *>(&Rw[r * TP_B + ((c2 + stage_rot(r)) & 31)]);
         }
         // ---- update the later columns:  acc[:, cb8] -= X[:, sb] * L[cb8 rows, sb cols]^T
         if (sb < TP_NSB - 1) {
             double af[8];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) af[ks] = -Rw[fr * TP_B + ks * 4 + fk];
+            for (int ks = 0; ks < 8; ++ks) af[ks] = -Rw[fr * TP_B + ((ks * 4 + fk + rot) & 31)];
 #pragma unroll
             for (int cb8 = (sb + 1) * 4; cb8 < TP_NC8; ++cb8) {
                 const double *Lq = Lb + lblk_index(cb8 >> 2, sb) * TP_LBLK + ((cb8 & 3) * 8 + fr) * TP_B + fk;

@@ -69,7 +69,7 @@ def test_cov_assemble_lower_only_and_jitter(gp, so):
 
 
 # ------------------------------------------------------------------ K3 batched Cholesky
-@pytest.mark.parametrize('n', [1, 5, 128, 129, 200, 384, 455, 1000])
+@pytest.mark.parametrize('n', [1, 5, 128, 129, 200, 257, 384, 385, 455, 1000])
 def test_potrf_batched_matches_lapack(gp, so, n):
     import torch
     import scipy.linalg
@@ -205,7 +205,9 @@ def test_loglik_matches_reference_curG_in_sds_fixtures(gp):
         np.testing.assert_allclose(ll[ok], z['trace_propG'][ok], rtol=RTOL_LOGLIK)
 
 
-@pytest.mark.parametrize('n,B', [(1000, 5), (2048, 3)])
+# sizes around the panel width: the border row that carries g (sequences.cu) lands in every position of the last row
+# tile / of the panel solve's last CTA (N = 128k, 128k + 1, 128k - 1, ragged)
+@pytest.mark.parametrize('n,B', [(1000, 5), (2048, 3), (127, 3), (128, 3), (129, 3), (256, 2), (257, 3), (385, 2), (641, 200)])
 def test_loglik_batched_vs_oracle_seeded(gp, so, n, B):
     x, _ = _series(gp, n)
     G, H = gp.synthetic.loglik_batch(B, n)
