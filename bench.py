@@ -284,7 +284,9 @@ def run_b200(args):
     # executed MACs of the update kernel: full 128-row tiles of every block column
     nb = gp._lib.load().gpmc_panel_width()                          # block-column width of this build (64 or 128)
     nt = (n + nb - 1) // nb
-    exec_flops = sum(2.0 * ((n - j * nb + 127) // 128 * 128) * nb * (j * nb) for j in range(1, nt))
+    # DMMA flops the update kernel really issues per factorisation: full 128-row tiles below the diagonal block, 8.5 of
+    # the 16 32x32 sub-tiles of the diagonal block (6 skipped, 4 at 10/16), one 8-row fragment for the border row
+    exec_flops = sum(2.0 * (j * nb) * nb * (((n - j * nb - nb + 127) // 128 * 128) + 0.53125 * nb + 8) for j in range(1, nt))
     peak = peaks.get('cublas_dgemm_8192_tflops')
     roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
