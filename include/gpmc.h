@@ -25,6 +25,12 @@
  *  - hyper-parameter rows are natural scale, hyp[b] = (ell_1..ell_E, sf, sn)
  *    with E = 1 (GPMC_KIND_SE_ISO, the reference's covK.RBF) or E = D
  *    (GPMC_KIND_SE_ARD); P = E + 2.
+ *  - threading: like the reference (one Python thread, sliceSample.py uses the
+ *    global numpy RNG) the library is meant for ONE host thread per process and
+ *    one process per GPU; it keeps per-process state (side streams and events of
+ *    the look-ahead schedule, the host-path staging buffers, the last-error text)
+ *    and is not re-entrant.  Calls are asynchronous on `stream` except where a
+ *    jitter policy needs info[] on the host (one synchronisation per wave).
  */
 #ifndef GPMC_H
 #define GPMC_H
