@@ -238,7 +238,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
     double *jit_dev = (double *)wp; wp += align_up((size_t)B * sizeof(double), 256);
     int *map_dev = (int *)wp; wp += align_up((size_t)B * sizeof(int), 256);
     wp += 256;
-    double *zscratch = (double *)wp; wp += align_up((size_t)32 * l.ld * sizeof(double), 256);
+    wp += align_up((size_t)32 * l.ld * sizeof(double), 256);      // (reserved: vector scratch)
     const size_t wave_cap = (ws_bytes - l.fixed_bytes) / l.per_item_bytes;
     const int wave = (int)std::min<size_t>(wave_cap, (size_t)B);
     double *mats = (double *)wp;

@@ -5,7 +5,8 @@
 // :122/:147) the device does, for every active chain at once:
 //     K+S (lower)            cov_assemble                                  :136-137,183-190
 //     L = chol(K+S)          potrf_sequence (+ pyGPs jitter ladder)        :196
-//     z = L^-1 g, log N(g)   solve_reduce                                  :147
+//     z = L^-1 g, log N(g)   g rides through potrf_sequence as a border    :147
+//                            row; border_finish (last block, quad form)
 //     U = L^-T               inverse_sequence
 //     m = g - S (U z)        trmv (upper)        == R S^-1 g               :204
 //     R = S - S (U U^T) S    r_sequence          == K - V^T V, V = L^-1 K  :197-198   (+1e-11 I, :205)
