@@ -389,6 +389,7 @@ int gpmc_set_tuning(int key, int value)
     if (key == 1) { set_potf2_mode(value); return 0; }
     if (key == 2) { set_lookahead_mode(value); return 0; }
     if (key == 3) { set_potrf_window(value); return 0; }
+    if (key == 4) { set_trsm_mode(value); return 0; }
     return GPMC_EINVAL;
 }
 

@@ -109,6 +109,9 @@ void set_potf2_mode(int mode);     // 0 auto (lite when the full inverse is not 
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
+// trsm_panel8.cu : the same solve with 8-column sub-blocks, shuffle-based fragment conversion, 2 CTAs per SM (default)
+int launch_trsm_panel8(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
+void set_trsm_mode(int mode);      // 0: trsm_panel8 (default), 1: trsm_panel (32-column sub-blocks)
 
 // solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)
 //   a, b, zout are per-item vectors with row stride ldv (b, zout, loglik may be nullptr)

@@ -174,6 +174,8 @@ static int potrf_window_for(int n, int B)
     return n >= 8192 ? 1024 : 512;
 }
 
+static int g_trsm_mode = 0;
+void set_trsm_mode(int mode) { g_trsm_mode = mode; }
 static int g_potf2_mode = 0;
 void set_potf2_mode(int mode) { g_potf2_mode = mode; }
 
@@ -286,7 +288,8 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
                       : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP);
             if (rc) return rc;
-            if (j0 + NB < n && (rc = launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP))) return rc;
+            if (j0 + NB < n && (rc = (g_trsm_mode == 1 ? launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP)
+                                                        : launch_trsm_panel8(A, nr, j0, Wj, strideW, B, sP)))) return rc;
             if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
         }
         if (la) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sG, la->ev_p, 0));                            // join

@@ -1,0 +1,168 @@
+// Panel triangular solve, second form:  X L11^T = A21  with 8-column sub-blocks (trsm_panel.cu works on 32).
+//
+// Same numerics as trsm_panel.cu -- per sub-block an inverse-multiply plus ONE step of iterative refinement against the
+// diagonal block itself,  X0 = A W8^T,  r = A - X0 L8^T,  X = X0 + r W8^T  (W8 = the 8x8 diagonal block of L11^-1, which
+// is the inverse of the 8x8 diagonal block of L11) -- but with the three small products done on 8x8 blocks the
+// triangular waste of the 32-wide products is gone: 336 DMMAs per 8 rows x 128 columns instead of 432, and the part
+// that remains is the plain update  acc[:, later] -= X_b L[later, b]^T.
+//
+// A warp owns 8 rows x 128 columns as DMMA accumulator fragments.  Fragment-layout changes (accumulator -> A operand)
+// are done with warp shuffles inside the 4-lane groups that share a row, and finished columns go to global memory
+// straight from the accumulator registers, so the CTA needs shared memory only for L11 and the sixteen W8 blocks
+// (100 KB): TWO CTAs of 64 rows share an SM and one CTA's prologue (loading L11) hides behind the other's DMMA stream.
+#include "common.cuh"
+#include "../../include/gpmc.h"
+
+namespace gpmc {
+
+constexpr int T8_ROWS = 64;                   // rows per CTA (8 warps x 8 rows)
+constexpr int T8_WARPS = T8_ROWS / 8 + 1;     // + one warp for a border row that follows a full last CTA
+constexpr int T8_THREADS = T8_WARPS * 32;
+constexpr int T8_B = 36;                      // row stride of a 32x32 L block (4 mod 16: conflict-free DMMA fragments)
+constexpr int T8_LBLK = 32 * T8_B;
+constexpr int T8_NSB = NB / 32;
+constexpr int T8_NLB = T8_NSB * (T8_NSB + 1) / 2;
+constexpr int T8_NB8 = NB / 8;                // 8-column sub-blocks
+constexpr int T8_WS = 12;                     // row stride of an 8x8 W block (conflict-free B fragments)
+constexpr int T8_SMEM = (T8_NLB * T8_LBLK + T8_NB8 * 8 * T8_WS) * (int)sizeof(double);
+
+__device__ __forceinline__ int lblk8_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
+
+__device__ __forceinline__ void dmma884_8(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// accumulator layout (row fr; columns 2fk, 2fk+1) -> A-operand layout (row fr; k = fk and k = fk + 4) of an 8x8 block
+__device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double &a0, double &a1)
+{
+    const int fk = lane & 3, base = lane & ~3;
+    const double p0 = __shfl_sync(0xffffffffu, c0, base | (fk >> 1));
+    const double p1 = __shfl_sync(0xffffffffu, c1, base | (fk >> 1));
+    const double q0 = __shfl_sync(0xffffffffu, c0, base | 2 | (fk >> 1));
+    const double q1 = __shfl_sync(0xffffffffu, c1, base | 2 | (fk >> 1));
+    a0 = (fk & 1) ? p1 : p0;
+    a1 = (fk & 1) ? q1 : q0;
+}
+
+__global__ void __launch_bounds__(T8_THREADS, 2)
+trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW)
+{
+    extern __shared__ __align__(16) double sm[];
+    double *Lb = sm;                              // 10 lower 32x32 blocks of L11
+    double *W8 = sm + T8_NLB * T8_LBLK;           // 16 diagonal 8x8 blocks of L11^-1, [blk][8][T8_WS]
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    double *Ab = A.base + (size_t)m * A.stride;
+    const int ld = A.ld;
+    const int row0 = j0 + NB + blockIdx.x * T8_ROWS;
+    // n_rows counts a border row too; the last CTA takes every row that is left (at most 64 + 1)
+    const int rows_valid = (blockIdx.x == gridDim.x - 1) ? min(T8_ROWS + 8, n_rows - row0) : T8_ROWS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+
+    for (int e = tid; e < T8_NLB * 32 * 16; e += T8_THREADS) {        // 16 16-byte pieces per block row
+        const int blk = e / (32 * 16), rem = e - blk * 32 * 16;
+        const int r = rem / 16, c2 = (rem - r * 16) * 2;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+        const int bj = blk - bi * (bi + 1) / 2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&Lb[blk * T8_LBLK + r * T8_B + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2));
+    }
+    const double *Wb = W + (size_t)m * strideW;
+    for (int e = tid; e < T8_NB8 * 8 * 4; e += T8_THREADS) {          // 4 pieces per row of an 8x8 block
+        const int blk = e >> 5, r = (e >> 2) & 7, c2 = (e & 3) * 2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&W8[(blk * 8 + r) * T8_WS + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wb + (size_t)(blk * 8 + r) * NB + blk * 8 + c2));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    // this warp's 8 rows as accumulator fragments: acc[b8] = row warp*8 + fr, cols b8*8 + 2fk, +1
+    double acc[T8_NB8][2];
+    const int r_loc = warp * 8 + fr;
+    double *grow = Ab + (size_t)(row0 + min(r_loc, max(rows_valid, 1) - 1)) * ld + j0 + 2 * fk;
+    {
+#pragma unroll
+        for (int b8 = 0; b8 < T8_NB8; ++b8) {
+            double2 v = make_double2(0.0, 0.0);
+            if (r_loc < rows_valid) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
+            acc[b8][0] = v.x;
+            acc[b8][1] = v.y;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    // the strict upper triangle of the diagonal blocks is garbage in global memory (L) or must read as zero (W8)
+    for (int e = tid; e < T8_NSB * 32 * 32; e += T8_THREADS) {
+        const int d = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        if (c > r) Lb[lblk8_index(d, d) * T8_LBLK + r * T8_B + c] = 0.0;
+    }
+    for (int e = tid; e < T8_NB8 * 64; e += T8_THREADS) {
+        const int blk = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        if (c > r) W8[(blk * 8 + r) * T8_WS + c] = 0.0;
+    }
+    __syncthreads();
+    if (warp * 8 >= rows_valid) return;           // nothing to solve (no border row, or a ragged last CTA)
+
+#pragma unroll
+    for (int b8 = 0; b8 < T8_NB8; ++b8) {
+        const int sb = b8 >> 2, q = b8 & 3;
+        // B fragments of the diagonal 8x8 blocks: element [c = fr][k = 4s + fk]
+        const double *Wq = W8 + (b8 * 8 + fr) * T8_WS + fk;
+        const double *Lq = Lb + lblk8_index(sb, sb) * T8_LBLK + (q * 8 + fr) * T8_B + q * 8 + fk;
+        const double w0 = Wq[0], w1 = Wq[4], l0 = Lq[0], l1 = Lq[4];
+        double a0, a1;
+        // ---- X0 = A W8^T
+        c_to_a(acc[b8][0], acc[b8][1], lane, a0, a1);
+        double x0 = 0.0, x1 = 0.0;
+        dmma884_8(x0, x1, a0, w0);
+        dmma884_8(x0, x1, a1, w1);
+        // ---- r = A - X0 L8^T
+        c_to_a(x0, x1, lane, a0, a1);
+        double r0 = acc[b8][0], r1 = acc[b8][1];
+        dmma884_8(r0, r1, -a0, l0);
+        dmma884_8(r0, r1, -a1, l1);
+        // ---- X = X0 + r W8^T   (one step of iterative refinement)
+        c_to_a(r0, r1, lane, a0, a1);
+        dmma884_8(x0, x1, a0, w0);
+        dmma884_8(x0, x1, a1, w1);
+        acc[b8][0] = x0; acc[b8][1] = x1;
+        // ---- later columns:  acc[:, b'] -= X L[b', b8]^T   (the next block first: it is the one the chain waits for)
+        if (b8 < T8_NB8 - 1) {
+            c_to_a(x0, x1, lane, a0, a1);
+            a0 = -a0; a1 = -a1;
+#pragma unroll
+            for (int bp = b8 + 1; bp < T8_NB8; ++bp) {
+                const double *Lp = Lb + lblk8_index(bp >> 2, sb) * T8_LBLK + ((bp & 3) * 8 + fr) * T8_B + q * 8 + fk;
+                dmma884_8(acc[bp][0], acc[bp][1], a0, Lp[0]);
+                dmma884_8(acc[bp][0], acc[bp][1], a1, Lp[4]);
+            }
+        }
+        // ---- the finished 8 columns leave from the accumulator registers (4 lanes x 16 bytes per row)
+        if (r_loc < rows_valid) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
+    }
+}
+
+int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s)
+{
+    int rows = n_rows - j0 - NB;
+    if (B <= 0 || rows <= 0) return 0;
+    if ((A.ld & 1) || (j0 & 1)) { set_error("trsm_panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
+    if (rows > 1 && rows % T8_ROWS == 1) rows -= 1;         // 64 k + 1: the extra row rides in the last CTA
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPMC_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((rows + T8_ROWS - 1) / T8_ROWS, B);
+    prof_begin(KC_TRSM, s);
+    trsm_panel8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n_rows, j0, W, strideW);
+    prof_end(KC_TRSM, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace gpmc

@@ -183,7 +183,8 @@ int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ld
  * key 1: panel factor kernel (0 auto, 1 always the full-inverse kernel, 2 the diagonal-inverse kernel whenever legal).
  * key 2: look-ahead in the blocked Cholesky (panel kernels overlapped with the update GEMM on side streams):
  *        0 auto (on when at most #SMs/2 matrices are in flight), 1 off, 2 on.
- * key 3: window (columns, multiple of 128) of the windowed schedule used for few large matrices; 0 = default. */
+ * key 3: window (columns, multiple of 128) of the windowed schedule used for few large matrices; 0 = default.
+ * key 4: panel solve kernel: 0 = 8-column sub-blocks, 2 CTAs/SM (default), 1 = 32-column sub-blocks. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:

@@ -136,6 +136,37 @@ def test_both_panel_factor_kernels_agree(gp, so, n):
         np.testing.assert_allclose(L2[b], L1[b], rtol=0, atol=1e-12 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize('n', [129, 193, 257, 300, 1000, 1153])
+def test_both_panel_solve_kernels_agree(gp, so, n):
+    """trsm_panel8.cu (8-column sub-blocks, 2 CTAs/SM, default) and trsm_panel.cu (32-column sub-blocks) solve the same
+    rows with the same inverse-multiply + refinement scheme; sizes put the last CTA at 1, 64, 65 and ragged row counts."""
+    import scipy.linalg
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    H = np.array([[1., 10., 1.2], [5., 4., 2.5], [0.35, 2., 0.2]])
+    A0 = gp.ops.cov_assemble(x, H, add_S=True)
+    Ah = A0.cpu().numpy()[:, :, :n]
+    G = np.random.RandomState(n).standard_normal((3, n))
+    out = {}
+    try:
+        for mode in (0, 1):
+            gp.ops.set_tuning(4, mode)
+            A = A0.clone()
+            info = gp.ops.potrf_batched(A, n=n, jitter_policy=gp.JITTER_NONE).cpu().numpy()
+            assert np.all(info == 0)
+            ll, _ = gp.ops.loglik_host(x, G, H)           # exercises the border row in the last CTA
+            out[mode] = (A.cpu().numpy()[:, :, :n], ll)
+    finally:
+        gp.ops.set_tuning(4, 0)
+    for b in range(3):
+        ref = scipy.linalg.cholesky(Ah[b], lower=True)
+        for mode in (0, 1):
+            L = out[mode][0][b]
+            assert np.linalg.norm(L @ L.T - Ah[b]) / np.linalg.norm(Ah[b]) < 5e-15
+            np.testing.assert_allclose(L, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+            want = so.loglik_unit(x, G[b], H[b], form='chol')
+            assert abs(out[mode][1][b] - want) <= RTOL_LOGLIK * abs(want)
+
+
 def test_potrf_jitter_ladder_matches_jitchol(gp):
     import torch
     from oracle import kcgp_shim
