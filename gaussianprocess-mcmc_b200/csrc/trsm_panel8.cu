@@ -10,6 +10,13 @@
 // are done with warp shuffles inside the 4-lane groups that share a row, and finished columns go to global memory
 // straight from the accumulator registers, so the CTA needs shared memory only for L11 and the sixteen W8 blocks
 // (100 KB): TWO CTAs of 64 rows share an SM and one CTA's prologue (loading L11) hides behind the other's DMMA stream.
+//
+// Measured alternatives (3 bench steps, N=4096 x 1024 chains; this form: 184 ms, trsm_panel.cu: 221 ms):
+//   * two 8-row fragments per warp (every B fragment from shared memory feeds two DMMAs, but only 8 working warps per
+//     SM): 210 ms -- slower, the per-block dependent chain needs the 16 warps;
+//   * solve chain of block b+1 interleaved in program order with the updates block b still owes: 184 ms -- no change,
+//     ptxas already schedules the fully unrolled block that way.
+// ncu: DMMA pipe 64 %, the rest is shared-memory pipe pressure (one 8-byte B-fragment load per DMMA plus the shuffles).
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
