@@ -6,17 +6,18 @@
 // triangular waste of the 32-wide products is gone: 336 DMMAs per 8 rows x 128 columns instead of 432, and the part
 // that remains is the plain update  acc[:, later] -= X_b L[later, b]^T.
 //
-// A warp owns 8 rows x 128 columns as DMMA accumulator fragments.  Fragment-layout changes (accumulator -> A operand)
-// are done with warp shuffles inside the 4-lane groups that share a row, and finished columns go to global memory
-// straight from the accumulator registers, so the CTA needs shared memory only for L11 and the sixteen W8 blocks
-// (100 KB): TWO CTAs of 64 rows share an SM and one CTA's prologue (loading L11) hides behind the other's DMMA stream.
+// A warp owns 8 rows x 128 columns as DMMA accumulator fragments.  The contraction index of an m8n8k4 DMMA may be
+// permuted freely as long as both operands agree, and an 8-wide block is exactly two k-steps of four lanes: with
+// step 0 taking k = 2 fk and step 1 taking k = 2 fk + 1, the two doubles a lane holds of an ACCUMULATOR fragment (row fr,
+// columns 2 fk and 2 fk + 1) ARE its A-operand fragments for the next product.  So the chain  X0 -> r -> X -> update  needs
+// no layout change at all (no shuffles, no shared-memory round trip), and the matching B fragments (W8[c][2fk], W8[c][2fk+1])
+// are adjacent in memory: one 16-byte load per pair of DMMAs.  Finished columns go to global memory straight from the
+// accumulator registers, so the CTA needs shared memory only for L11 and the sixteen W8 blocks (108 KB): TWO CTAs of
+// 64 rows share an SM and one CTA's prologue (loading L11) hides behind the other's DMMA stream.
 //
-// Measured alternatives (3 bench steps, N=4096 x 1024 chains; this form: 184 ms, trsm_panel.cu: 221 ms):
-//   * two 8-row fragments per warp (every B fragment from shared memory feeds two DMMAs, but only 8 working warps per
-//     SM): 210 ms -- slower, the per-block dependent chain needs the 16 warps;
-//   * solve chain of block b+1 interleaved in program order with the updates block b still owes: 184 ms -- no change,
-//     ptxas already schedules the fully unrolled block that way.
-// ncu: DMMA pipe 64 %, the rest is shared-memory pipe pressure (one 8-byte B-fragment load per DMMA plus the shuffles).
+// History (3 bench steps, N=4096 x 1024 chains): trsm_panel.cu (32-column sub-blocks, layout changes through shared
+// memory) 221 ms; 8-column sub-blocks with shuffle-based layout changes 184 ms (shared-memory-pipe bound: one 8-byte
+// B-fragment load per DMMA plus 504 shuffles per warp); two 8-row fragments per warp 210 ms (too few warps).
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
@@ -25,12 +26,12 @@ namespace gpmc {
 constexpr int T8_ROWS = 64;                   // rows per CTA (8 warps x 8 rows)
 constexpr int T8_WARPS = T8_ROWS / 8 + 1;     // + one warp for a border row that follows a full last CTA
 constexpr int T8_THREADS = T8_WARPS * 32;
-constexpr int T8_B = 36;                      // row stride of a 32x32 L block (4 mod 16: conflict-free DMMA fragments)
+constexpr int T8_B = 40;                      // row stride of a 32x32 L block (8 mod 16: conflict-free 16-byte fragment loads)
 constexpr int T8_LBLK = 32 * T8_B;
 constexpr int T8_NSB = NB / 32;
 constexpr int T8_NLB = T8_NSB * (T8_NSB + 1) / 2;
 constexpr int T8_NB8 = NB / 8;                // 8-column sub-blocks
-constexpr int T8_WS = 12;                     // row stride of an 8x8 W block (conflict-free B fragments)
+constexpr int T8_WS = 8;                      // row stride of an 8x8 W block (dense: conflict-free 16-byte fragment loads)
 constexpr int T8_SMEM = (T8_NLB * T8_LBLK + T8_NB8 * 8 * T8_WS) * (int)sizeof(double);
 
 __device__ __forceinline__ int lblk8_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }     // bi >= bj
@@ -40,18 +41,6 @@ __device__ __forceinline__ void dmma884_8(double &c0, double &c1, double a, doub
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
-}
-
-// accumulator layout (row fr; columns 2fk, 2fk+1) -> A-operand layout (row fr; k = fk and k = fk + 4) of an 8x8 block
-__device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double &a0, double &a1)
-{
-    const int fk = lane & 3, base = lane & ~3;
-    const double p0 = __shfl_sync(0xffffffffu, c0, base | (fk >> 1));
-    const double p1 = __shfl_sync(0xffffffffu, c1, base | (fk >> 1));
-    const double q0 = __shfl_sync(0xffffffffu, c0, base | 2 | (fk >> 1));
-    const double q1 = __shfl_sync(0xffffffffu, c1, base | 2 | (fk >> 1));
-    a0 = (fk & 1) ? p1 : p0;
-    a1 = (fk & 1) ? q1 : q0;
 }
 
 __global__ void __launch_bounds__(T8_THREADS, 2)
@@ -117,36 +106,28 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
 #pragma unroll
     for (int b8 = 0; b8 < T8_NB8; ++b8) {
         const int sb = b8 >> 2, q = b8 & 3;
-        // B fragments of the diagonal 8x8 blocks: element [c = fr][k = 4s + fk]
-        const double *Wq = W8 + (b8 * 8 + fr) * T8_WS + fk;
-        const double *Lq = Lb + lblk8_index(sb, sb) * T8_LBLK + (q * 8 + fr) * T8_B + q * 8 + fk;
-        const double w0 = Wq[0], w1 = Wq[4], l0 = Lq[0], l1 = Lq[4];
-        double a0, a1;
-        // ---- X0 = A W8^T
-        c_to_a(acc[b8][0], acc[b8][1], lane, a0, a1);
+        // B fragments of the diagonal 8x8 blocks: lane (c = fr, fk) takes [c][2fk] for k-step 0 and [c][2fk+1] for k-step 1
+        const double2 w = *reinterpret_cast<const double2 *>(W8 + (b8 * 8 + fr) * T8_WS + 2 * fk);
+        const double2 l = *reinterpret_cast<const double2 *>(Lb + lblk8_index(sb, sb) * T8_LBLK + (q * 8 + fr) * T8_B + q * 8 + 2 * fk);
+        // ---- X0 = A W8^T   (the accumulator pair is the A operand of the two k-steps)
         double x0 = 0.0, x1 = 0.0;
-        dmma884_8(x0, x1, a0, w0);
-        dmma884_8(x0, x1, a1, w1);
+        dmma884_8(x0, x1, acc[b8][0], w.x);
+        dmma884_8(x0, x1, acc[b8][1], w.y);
         // ---- r = A - X0 L8^T
-        c_to_a(x0, x1, lane, a0, a1);
         double r0 = acc[b8][0], r1 = acc[b8][1];
-        dmma884_8(r0, r1, -a0, l0);
-        dmma884_8(r0, r1, -a1, l1);
+        dmma884_8(r0, r1, -x0, l.x);
+        dmma884_8(r0, r1, -x1, l.y);
         // ---- X = X0 + r W8^T   (one step of iterative refinement)
-        c_to_a(r0, r1, lane, a0, a1);
-        dmma884_8(x0, x1, a0, w0);
-        dmma884_8(x0, x1, a1, w1);
+        dmma884_8(x0, x1, r0, w.x);
+        dmma884_8(x0, x1, r1, w.y);
         acc[b8][0] = x0; acc[b8][1] = x1;
         // ---- later columns:  acc[:, b'] -= X L[b', b8]^T   (the next block first: it is the one the chain waits for)
-        if (b8 < T8_NB8 - 1) {
-            c_to_a(x0, x1, lane, a0, a1);
-            a0 = -a0; a1 = -a1;
+        const double nx0 = -x0, nx1 = -x1;
 #pragma unroll
-            for (int bp = b8 + 1; bp < T8_NB8; ++bp) {
-                const double *Lp = Lb + lblk8_index(bp >> 2, sb) * T8_LBLK + ((bp & 3) * 8 + fr) * T8_B + q * 8 + fk;
-                dmma884_8(acc[bp][0], acc[bp][1], a0, Lp[0]);
-                dmma884_8(acc[bp][0], acc[bp][1], a1, Lp[4]);
-            }
+        for (int bp = b8 + 1; bp < T8_NB8; ++bp) {
+            const double2 lp = *reinterpret_cast<const double2 *>(Lb + lblk8_index(bp >> 2, sb) * T8_LBLK + ((bp & 3) * 8 + fr) * T8_B + q * 8 + 2 * fk);
+            dmma884_8(acc[bp][0], acc[bp][1], nx0, lp.x);
+            dmma884_8(acc[bp][0], acc[bp][1], nx1, lp.y);
         }
         // ---- the finished 8 columns leave from the accumulator registers (4 lanes x 16 bytes per row)
         if (r_loc < rows_valid) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
