@@ -352,6 +352,31 @@ def test_lookahead_schedule_equals_sequential_schedule(gp, so, n, B):
         assert abs(out[2][b] - ref) <= RTOL_LOGLIK * abs(ref)
 
 
+def test_loglik_random_shapes_against_oracle(gp, so):
+    """Seeded sweep over ragged shapes: every (N, B) picks its own mix of schedules (left-looking / windowed, look-ahead
+    on or off, either panel factor kernel, border row in any position of the last tile) -- all must match the oracle."""
+    rs = np.random.RandomState(20261018)
+    worst = 0.0
+    for case in range(28):
+        n = int(rs.choice([rs.randint(1, 130), rs.randint(130, 400), rs.randint(400, 900)]))
+        B = int(rs.choice([1, 2, 3, 7, 33, 160]))
+        d = int(rs.choice([1, 1, 2, 3]))
+        ard = d > 1 and bool(rs.randint(2))
+        x = np.sort(rs.uniform(0, n, size=(n, d)), axis=0) if d > 1 else np.arange(n, dtype=np.float64).reshape(n, 1)
+        G, H = gp.synthetic.loglik_batch(B, n, n_ell=d if ard else 1)
+        ll, info = gp.ops.loglik_host(x, G, H)
+        assert np.all(info == 0), (n, B, d, ard)
+        for b in sorted(set([0, B - 1, B // 2])):
+            ref = so.loglik_unit(x, G[b], H[b], form='chol')
+            rel = abs(ll[b] - ref) / abs(ref)
+            K = so.cov_matrix(x, H[b])
+            cond = np.linalg.cond(K + np.diag(so.s_diagonal(np.diagonal(K), H[b, -1])))
+            tol = max(RTOL_LOGLIK, 1.1e-16 * cond)          # the conditioning limit of the quantity itself (DESIGN.md section 4)
+            worst = max(worst, rel / tol)
+            assert rel <= tol, (n, B, d, ard, b, rel, cond)
+    print('random shapes: worst error / tolerance', worst)
+
+
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
     """The DMMA tile kernel exists in four variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
