@@ -86,8 +86,6 @@ struct GemmArgs {
     int epi;               // Epilogue
     int skip_upper;        // C's strict upper triangle (global row < global col) is never read by the caller: warps whose
                            // whole sub-tile lies there may skip their contraction and leave C untouched
-    int in_place;          // C overlaps A's contraction range (C = -(C W^T) in inverse_sequence): ONE CTA must own all columns
-                           // of its rows and finish reading them before it writes -> 128-column tile kernel, cols <= 128
     int border_row;        // > 0 (EPI_SUB, skip_upper, cr0 == cc0, A == C buffers): global row of a right-hand side carried as a
                            // ROW below the matrix; it receives the same update, C[border_row, cols] -= A[border_row, k] B[cols, k]^T
     const double *svec;    // EPI_R: per-item diagonal of S, [N]
@@ -111,6 +109,9 @@ void set_potf2_mode(int mode);     // 0 auto (lite when the full inverse is not 
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
 // trsm_panel8.cu : the same solve with 8-column sub-blocks, shuffle-based fragment conversion, 2 CTAs per SM (default)
 int launch_trsm_panel8(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
+// trmm_panel8.cu : in place  A[0:rows, c0:c0+width] = -(A[0:rows, c0:c0+128] W^T)  for a lower triangular 128x128 W
+//   (the second product of the triangular inverse, inverse_sequence)
+int launch_trmm_panel8(BatchView A, int rows, int c0, int width, const double *W, long long strideW, int B, cudaStream_t s);
 void set_trsm_mode(int mode);      // 0: trsm_panel8 (default), 1: trsm_panel (32-column sub-blocks)
 
 // solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)

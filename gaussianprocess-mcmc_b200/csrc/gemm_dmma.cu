@@ -173,12 +173,6 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
         if (e && e[0] >= '0' && e[0] <= '4') g_gemm_cfg = e[0] - '0';
         env_read = true;
     }
-    if (a.in_place) {
-        // every variant reads its whole K range (cp_async_wait<0>) before the epilogue writes; with a 128-column tile no
-        // other CTA touches these rows, so updating C in place of its own A operand is race free
-        if (a.cols > 128 || a.lower_only || a.border_row) { set_error("gemm: in-place product needs cols <= 128 (cols=%d)", a.cols); return GPMC_EINVAL; }
-        return launch_variant(gemm_dmma_kernel<4, 4, 128, 4, 1>, a, B, 128, 512, gemm_smem_bytes(128, 4), kclass, s, set1);
-    }
     const bool border_fusable = a.border_row == 0 || (a.skip_upper && a.epi == EPI_SUB && a.cr0 == a.cc0 && a.A.base == a.C.base);
     if (g_gemm_cfg == 4 && gemm_tma_supported(a) && border_fusable) return launch_gemm_tma(a, B, kclass, true, s);   // border row fused in-kernel
     if (a.border_row > 0) {

@@ -384,13 +384,8 @@ int inverse_sequence(BatchView A, int n, int B, const double *W, long long strid
             g.epi = EPI_SET;
             int rc = launch_gemm(g, B, KC_INV, s);
             if (rc) return rc;
-            GemmArgs h{};
-            h.C = A; h.A = self; h.B = Operand{Wi, strideW, NB};
-            h.cr0 = 0; h.cc0 = i0; h.rows = i0; h.cols = width;
-            h.ar0 = 0; h.br0 = 0; h.k0 = i0; h.bk0 = 0; h.klen = (width + 15) & ~15;   // stays inside ld (pads are zero)
-            h.epi = EPI_NEGSET;
-            h.in_place = 1;                             // Y is overwritten by -(Y W_i^T)
-            rc = launch_gemm(h, B, KC_INV, s);
+            // U[0:i0, i] = -(Y W_i^T), in place (every warp of the panel kernel reads its rows before it writes them)
+            rc = launch_trmm_panel8(A, i0, i0, width, Wi, strideW, B, s);
             if (rc) return rc;
         }
         prof_begin(KC_INV, s);
