@@ -97,8 +97,8 @@ void set_gemm_config(int cfg);
 // potf2.cu : factor the NB x NB diagonal block at (j0, j0) in place, write its inverse to W
 int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                  int B, cudaStream_t s);
-// potf2_lite.cu : same factor, but only the inverses of the four 32x32 diagonal sub-blocks are written to W (all that
-// launch_trsm_panel reads); 2 CTAs per SM.  Not for callers that go on to inverse_sequence.
+// potf2_lite.cu : same factor, but only the inverses of the sixteen 8x8 diagonal sub-blocks are written to W (all that
+// launch_trsm_panel8 reads); 2 CTAs per SM.  Not for callers that go on to inverse_sequence or use launch_trsm_panel.
 int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                       int B, cudaStream_t s);
 void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on

@@ -1,31 +1,37 @@
-// Panel kernel without the full inverse: factor one 128x128 diagonal block and emit only the inverses of its four
-// 32x32 diagonal sub-blocks (all that trsm_panel.cu needs).  Used wherever the caller does not go on to invert the
+// Panel kernel without the block inverse: factor one 128x128 diagonal block and emit only the inverses of its sixteen
+// 8x8 diagonal sub-blocks (all that trsm_panel8.cu needs).  Used wherever the caller does not go on to invert the
 // factor: the log-likelihood unit (sliceSample.py:196,147) and chol(R + 1e-11 I) (sliceSample.py:205).
 //
-// Same scheme as potf2.cu -- ONE warp factors each 32x32 diagonal sub-block with a matrix row (and an identity row)
-// per lane in registers and warp-shuffle broadcasts; sub-panel rows are solved by inverse-multiply + one refinement
-// step, trailing sub-blocks are updated, both on FP64 DMMA -- but only the lower triangle is kept in shared memory
-// (block rows of growing length: 86 KB instead of 135 KB) and the CTA has 4 warps, so TWO CTAs share an SM: the
-// kernel is latency bound (one CTA per matrix), and a second resident CTA nearly doubles the batched throughput.
+// Same scheme as potf2.cu -- ONE warp factors each 32x32 diagonal sub-block with a matrix row per lane in registers and
+// warp-shuffle broadcasts of pivots and multipliers -- with three differences:
+//  * the identity rows that ride along (the inverse) are updated only inside their own 8-column micro-block: the 8x8
+//    diagonal inverses are all anyone needs, and the full 32x32 inverse costs as many DFMAs as the factor itself;
+//  * sub-panel rows are solved and trailing sub-blocks are updated on FP64 DMMA with the contraction index permuted
+//    (k-step 0 takes k = 2 fk, k-step 1 takes k = 2 fk + 1): accumulator pairs are the next A operands and every
+//    operand is one 16-byte shared-memory access -- no fragment-layout changes, no warp synchronisation; the solve is
+//    the 8-column inverse-multiply + one refinement step of trsm_panel8.cu;
+//  * only the lower triangle is kept in shared memory (block rows of growing length: 90 KB instead of 135 KB) and the
+//    CTA has 4 warps, so TWO CTAs share an SM: the kernel is latency bound (one CTA per matrix), and a second resident
+//    CTA nearly doubles the batched throughput.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
 
 constexpr int QB = 32;                        // inner block
-constexpr int QC = 36;                        // row stride of the clean 32x32 inverse
 constexpr int LITE_THREADS = 128;
 constexpr int LITE_WARPS = LITE_THREADS / 32;
 constexpr int LITE_NBLK = NB / QB;            // block rows (4 for a 128 panel)
-// lower-triangular storage: block row bi keeps 32*(bi+1) columns, row stride 32*(bi+1) + 4 (4 mod 16: conflict-free
-// DMMA fragments); doubles before block row bi = 512*bi*(bi+1) + 128*bi
-constexpr int LITE_T_ELEMS = 512 * LITE_NBLK * (LITE_NBLK + 1) + 128 * LITE_NBLK;
-constexpr int LITE_SMEM = (LITE_T_ELEMS + QB * QC + NB) * (int)sizeof(double);
+// lower-triangular storage: block row bi keeps 32*(bi+1) columns, row stride 32*(bi+1) + 8 (8 mod 16: conflict-free
+// 16-byte DMMA fragment accesses); doubles before block row bi = 512*bi*(bi+1) + 256*bi
+constexpr int LITE_T_ELEMS = 512 * LITE_NBLK * (LITE_NBLK + 1) + 256 * LITE_NBLK;
+constexpr int LITE_W8_ELEMS = (QB / 8) * 8 * 8;      // the four 8x8 diagonal inverses of the current 32x32 sub-block
+constexpr int LITE_SMEM = (LITE_T_ELEMS + LITE_W8_ELEMS) * (int)sizeof(double);
 
 __device__ __forceinline__ int tix(int r, int c)
 {
     const int bi = r >> 5;
-    return 512 * bi * (bi + 1) + 128 * bi + (r & 31) * (32 * (bi + 1) + 4) + c;
+    return 512 * bi * (bi + 1) + 256 * bi + (r & 31) * (32 * (bi + 1) + 8) + c;
 }
 
 __device__ __forceinline__ void dmma884_l(double &c0, double &c1, double a, double b)
@@ -40,7 +46,7 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
 {
     extern __shared__ __align__(16) double sm[];
     double *T = sm;                           // lower triangle, block rows
-    double *Lc = sm + LITE_T_ELEMS;           // [QB][QC] inverse of the current diagonal sub-block
+    double *W8 = sm + LITE_T_ELEMS;           // [4][8][8] diagonal 8x8 inverses of the current sub-block, [blk][c][k]
     __shared__ int s_fail;
     const int b = blockIdx.x;
     if (A.count && b >= *A.count) return;
@@ -74,16 +80,23 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
     __syncthreads();
 
     double *Wb = W + (size_t)m * strideW;
+#pragma unroll 1
     for (int kb = 0; kb < LITE_NBLK; ++kb) {
         const int k0 = kb * QB;
         // ---------------------------------------------------------------- 32x32 diagonal sub-block, one warp
         if (warp == 0) {
             double a[QB], x[QB];
+            {
+                const double *row = &T[tix(k0 + lane, k0)];
 #pragma unroll
-            for (int c = 0; c < QB; ++c) {
-                a[c] = (c <= lane) ? T[tix(k0 + lane, k0 + c)] : 0.0;
-                x[c] = (c == lane) ? 1.0 : 0.0;
+                for (int c = 0; c < QB; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(row + c);
+                    a[c] = (c <= lane) ? v.x : 0.0;
+                    a[c + 1] = (c + 1 <= lane) ? v.y : 0.0;
+                }
             }
+#pragma unroll
+            for (int c = 0; c < QB; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
             int fail = 0;
 #pragma unroll
             for (int q = 0; q < QB / 8; ++q) {
@@ -99,7 +112,7 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
                     for (int j = c + 1; j < q * 8 + 8; ++j) {
                         const double ljc = __shfl_sync(0xffffffffu, a[c], j);
                         a[j] = fma(-a[c], ljc, a[j]);
-                        x[j] = fma(-x[c], ljc, x[j]);
+                        x[j] = fma(-x[c], ljc, x[j]);          // stays inside the micro-block: the 8x8 diagonal inverse
                     }
                 }
 #pragma unroll
@@ -108,68 +121,63 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
                     for (int c = q * 8; c < q * 8 + 8; ++c) {
                         const double ljc = __shfl_sync(0xffffffffu, a[c], j);
                         a[j] = fma(-a[c], ljc, a[j]);
-                        x[j] = fma(-x[c], ljc, x[j]);
                     }
                 }
             }
-            // L_d (lower, zeros above) back into T; its inverse Lc[c][k] = X[k][c] to shared memory and to W's diagonal
+            // L_d (lower, zeros above) back into T; the 8x8 diagonal inverses W8[blk][c][k] = x_k[c] (k <= c, same
+            // micro-block) to shared memory and to the diagonal of W in global memory
+            {
+                double *row = &T[tix(k0 + lane, k0)];
+#pragma unroll
+                for (int c = 0; c < QB; c += 2)
+                    *reinterpret_cast<double2 *>(row + c) = make_double2((c <= lane) ? a[c] : 0.0, (c + 1 <= lane) ? a[c + 1] : 0.0);
+            }
+            const int qb = lane >> 3, kl = lane & 7;
 #pragma unroll
             for (int c = 0; c < QB; ++c) {
-                T[tix(k0 + lane, k0 + c)] = (c <= lane) ? a[c] : 0.0;
-                const double w = (lane <= c) ? x[c] : 0.0;
-                Lc[c * QC + lane] = w;
-                Wb[(k0 + c) * NB + k0 + lane] = w;
+                if ((c >> 3) == qb) {
+                    const double w = (kl <= (c & 7)) ? x[c] : 0.0;
+                    W8[(qb * 8 + (c & 7)) * 8 + kl] = w;
+                    Wb[(k0 + c) * NB + k0 + qb * 8 + kl] = w;
+                }
             }
             if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;
         }
         __syncthreads();
-        // ---------------------------------------------------------------- sub-panel rows below: X0 = A Lc^T,
-        //   r = A - X0 L_d^T, X = X0 + r Lc^T   (inverse-multiply + one refinement step, see trsm_panel.cu)
+        // ---------------------------------------------------------------- sub-panel rows below, 8 rows x 32 columns
+        //   per unit: per 8-column block  X0 = A W8^T, r = A - X0 L8^T, X = X0 + r W8^T, later blocks -= X L^T
         {
-            const int nblk_below = (NB - k0 - QB) / 8;
-            for (int u = warp; u < nblk_below; u += LITE_WARPS) {
-                const int r0 = k0 + QB + u * 8;
-                double *row = &T[tix(r0 + fr, k0)];
-                double fa[8], a0[4][2], x0[4][2], rr[4][2];
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) fa[ks] = row[ks * 4 + fk];
+            const int nunits = (NB - k0 - QB) / 8;
+            for (int u = warp; u < nunits; u += LITE_WARPS) {
+                double *row = &T[tix(k0 + QB + u * 8 + fr, k0 + 2 * fk)];
+                double acc[4][2];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double2 t2 = *reinterpret_cast<const double2 *>(row + q * 8 + 2 * fk);
-                    a0[q][0] = t2.x; a0[q][1] = t2.y;
-                    x0[q][0] = x0[q][1] = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks <= 2 * q + 1; ++ks)
-                        dmma884_l(x0[q][0], x0[q][1], fa[ks], Lc[(q * 8 + fr) * QC + ks * 4 + fk]);
+                    const double2 v = *reinterpret_cast<const double2 *>(row + q * 8);
+                    acc[q][0] = v.x; acc[q][1] = v.y;
                 }
-                __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(row + q * 8 + 2 * fk) = make_double2(x0[q][0], x0[q][1]);
-                __syncwarp();
+                for (int bb = 0; bb < 4; ++bb) {
+                    const double2 w = *reinterpret_cast<const double2 *>(&W8[(bb * 8 + fr) * 8 + 2 * fk]);
+                    const double2 l = *reinterpret_cast<const double2 *>(&T[tix(k0 + bb * 8 + fr, k0 + bb * 8 + 2 * fk)]);
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma884_l(x0, x1, acc[bb][0], w.x);
+                    dmma884_l(x0, x1, acc[bb][1], w.y);
+                    double r0 = acc[bb][0], r1 = acc[bb][1];
+                    dmma884_l(r0, r1, -x0, l.x);
+                    dmma884_l(r0, r1, -x1, l.y);
+                    dmma884_l(x0, x1, r0, w.x);
+                    dmma884_l(x0, x1, r1, w.y);
+                    acc[bb][0] = x0; acc[bb][1] = x1;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) fa[ks] = -row[ks * 4 + fk];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    rr[q][0] = a0[q][0]; rr[q][1] = a0[q][1];
-#pragma unroll
-                    for (int ks = 0; ks <= 2 * q + 1; ++ks)                  // L_d is clean (zeros above its diagonal)
-                        dmma884_l(rr[q][0], rr[q][1], fa[ks], T[tix(k0 + q * 8 + fr, k0 + ks * 4 + fk)]);
+                    for (int q = bb + 1; q < 4; ++q) {
+                        const double2 lp = *reinterpret_cast<const double2 *>(&T[tix(k0 + q * 8 + fr, k0 + bb * 8 + 2 * fk)]);
+                        dmma884_l(acc[q][0], acc[q][1], -x0, lp.x);
+                        dmma884_l(acc[q][0], acc[q][1], -x1, lp.y);
+                    }
                 }
-                __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(row + q * 8 + 2 * fk) = make_double2(rr[q][0], rr[q][1]);
-                __syncwarp();
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) fa[ks] = row[ks * 4 + fk];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int ks = 0; ks <= 2 * q + 1; ++ks)
-                        dmma884_l(x0[q][0], x0[q][1], fa[ks], Lc[(q * 8 + fr) * QC + ks * 4 + fk]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(row + q * 8 + 2 * fk) = make_double2(x0[q][0], x0[q][1]);
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(row + q * 8) = make_double2(acc[q][0], acc[q][1]);
             }
         }
         __syncthreads();
@@ -182,19 +190,26 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
                 for (int rb = 0; rb < (NB - c0) / 8; ++rb, ++u) {
                     if ((u % LITE_WARPS) != warp) continue;
                     const int r0 = c0 + rb * 8;
-                    double af[8];
+                    double2 af[4];
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) af[ks] = -T[tix(r0 + fr, k0 + ks * 4 + fk)];
+                    for (int s = 0; s < 4; ++s) {
+                        af[s] = *reinterpret_cast<const double2 *>(&T[tix(r0 + fr, k0 + s * 8 + 2 * fk)]);
+                        af[s].x = -af[s].x; af[s].y = -af[s].y;
+                    }
+                    double *crow = &T[tix(r0 + fr, c0 + 2 * fk)];
                     double2 cv[4];
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) cv[c8] = *reinterpret_cast<const double2 *>(&T[tix(r0 + fr, c0 + c8 * 8 + 2 * fk)]);
+                    for (int c8 = 0; c8 < 4; ++c8) cv[c8] = *reinterpret_cast<const double2 *>(crow + c8 * 8);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
+                    for (int s = 0; s < 4; ++s)
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8)
-                            dmma884_l(cv[c8].x, cv[c8].y, af[ks], T[tix(c0 + c8 * 8 + fr, k0 + ks * 4 + fk)]);
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const double2 bf = *reinterpret_cast<const double2 *>(&T[tix(c0 + c8 * 8 + fr, k0 + s * 8 + 2 * fk)]);
+                            dmma884_l(cv[c8].x, cv[c8].y, af[s].x, bf.x);
+                            dmma884_l(cv[c8].x, cv[c8].y, af[s].y, bf.y);
+                        }
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<double2 *>(&T[tix(r0 + fr, c0 + c8 * 8 + 2 * fk)]) = cv[c8];
+                    for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<double2 *>(crow + c8 * 8) = cv[c8];
                 }
             }
         }

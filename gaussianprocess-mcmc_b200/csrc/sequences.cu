@@ -229,7 +229,8 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     if (border_rows < 0 || border_rows > 1) { set_error("potrf_sequence: at most one border row"); return GPMC_EINVAL; }
     const int nr = n + border_rows;                     // rows that take part in the panel solves
     // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
-    const bool lite = (w_step == 0) && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > sm_count()));
+    // (the lite kernel emits the 8x8 diagonal inverses only: enough for trsm_panel8, not for trsm_panel's 32x32 blocks)
+    const bool lite = (w_step == 0) && g_trsm_mode == 0 && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > sm_count()));
     const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
