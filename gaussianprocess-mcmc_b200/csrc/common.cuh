@@ -103,7 +103,7 @@ int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, 
                       int B, cudaStream_t s);
 void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on
 void set_potrf_window(int w);      // override the window of the windowed schedule (multiple of NB; 0 = default)
-void set_potf2_mode(int mode);     // 0 auto (lite when the full inverse is not needed and B > #SMs), 1 always full, 2 lite whenever legal
+void set_potf2_mode(int mode);     // 0 / 2: the lite kernel whenever the full inverse is not needed (default), 1: always the full one
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
@@ -112,6 +112,9 @@ int launch_trsm_panel8(BatchView A, int n, int j0, const double *W, long long st
 // trmm_panel8.cu : in place  A[0:rows, c0:c0+width] = -(A[0:rows, c0:c0+128] W^T)  for a lower triangular 128x128 W
 //   (the second product of the triangular inverse, inverse_sequence)
 int launch_trmm_panel8(BatchView A, int rows, int c0, int width, const double *W, long long strideW, int B, cudaStream_t s);
+// W_i = L_ii^-1 for every diagonal block of a factored matrix, from the 8x8 diagonal inverses potf2_lite left in W
+//   (W: nt blocks of NB x NB per item, item stride strideW)
+int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, cudaStream_t s);
 void set_trsm_mode(int mode);      // 0: trsm_panel8 (default), 1: trsm_panel (32-column sub-blocks)
 
 // solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)

@@ -178,6 +178,7 @@ static int g_trsm_mode = 0;
 void set_trsm_mode(int mode) { g_trsm_mode = mode; }
 static int g_potf2_mode = 0;
 void set_potf2_mode(int mode) { g_potf2_mode = mode; }
+static bool lite_panels() { return g_trsm_mode == 0 && g_potf2_mode != 1; }
 
 static int sm_count()
 {
@@ -229,8 +230,10 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     if (border_rows < 0 || border_rows > 1) { set_error("potrf_sequence: at most one border row"); return GPMC_EINVAL; }
     const int nr = n + border_rows;                     // rows that take part in the panel solves
     // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
-    // (the lite kernel emits the 8x8 diagonal inverses only: enough for trsm_panel8, not for trsm_panel's 32x32 blocks)
-    const bool lite = (w_step == 0) && g_trsm_mode == 0 && (g_potf2_mode == 2 || (g_potf2_mode == 0 && B > sm_count()));
+    // The lite kernel emits the 8x8 diagonal inverses only: enough for trsm_panel8 (not for trsm_panel's 32x32 blocks).
+    // Measured: it is the faster of the two at every batch size.  Callers that keep the block inverses (w_step != 0)
+    // get them completed by inverse_sequence (launch_inv_blocks8) from those 8x8 blocks.
+    const bool lite = lite_panels();
     const int window = potrf_window_for(n, B);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
@@ -372,6 +375,11 @@ int inverse_sequence(BatchView A, int n, int B, const double *W, long long strid
 {
     const int nt = (n + NB - 1) / NB;
     const Operand self{A.base, A.stride, A.ld};
+    if (lite_panels()) {
+        // the factorisation left only the 8x8 diagonal inverses in W: complete every W_i = L_ii^-1 in one launch
+        int rc = launch_inv_blocks8(A, n, const_cast<double *>(W), strideW, B, s);
+        if (rc) return rc;
+    }
     for (int i = 0; i < nt; ++i) {
         const int i0 = i * NB;
         const int width = std::min(NB, n - i0);

@@ -134,6 +134,117 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Block inverses for inverse_sequence:  W_i = L_ii^-1 for every 128x128 diagonal block of a factored matrix, from the
+// 8x8 diagonal inverses the panel factor kernel left in W.  It is the same solve run on the identity:
+// Y L_ii^T = I  gives  Y = L_ii^-T = W_i^T  (one refinement step included), stored transposed.  One launch covers all
+// blocks of all matrices (2 CTAs of 64 identity rows per block); the 8x8 diagonal blocks of W are kept as they are, so
+// the two CTAs of a block never write what the other one reads.
+__global__ void __launch_bounds__(T8_THREADS, 2)
+inv_blocks8_kernel(BatchView A, int n, double *__restrict__ W, long long strideW)
+{
+    extern __shared__ __align__(16) double sm[];
+    double *Lb = sm;
+    double *W8 = sm + T8_NLB * T8_LBLK;
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const int blk_i = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int i0 = blk_i * NB;
+    const int nv = min(NB, n - i0);               // rows/cols of this diagonal block that exist
+    const double *Ab = A.base + (size_t)m * A.stride;
+    const int ld = A.ld;
+    double *Wi = W + (size_t)m * strideW + (size_t)blk_i * NB * NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+
+    for (int e = tid; e < T8_NLB * 32 * 16; e += T8_THREADS) {
+        const int blk = e / (32 * 16), rem = e - blk * 32 * 16;
+        const int r = rem / 16, c2 = (rem - r * 16) * 2;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+        const int bj = blk - bi * (bi + 1) / 2;
+        const int gr = bi * 32 + r, gc = bj * 32 + c2;
+        double *dstp = &Lb[blk * T8_LBLK + r * T8_B + c2];
+        if (gr < nv && gc < nv) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dstp);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)(i0 + gr) * ld + i0 + gc));
+        } else {                                  // beyond the matrix: identity
+            dstp[0] = (gr == gc) ? 1.0 : 0.0;
+            dstp[1] = (gr == gc + 1) ? 1.0 : 0.0;
+        }
+    }
+    for (int e = tid; e < T8_NB8 * 8 * 4; e += T8_THREADS) {
+        const int blk = e >> 5, r = (e >> 2) & 7, c2 = (e & 3) * 2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&W8[(blk * 8 + r) * T8_WS + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wi + (size_t)(blk * 8 + r) * NB + blk * 8 + c2));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    for (int e = tid; e < T8_NSB * 32 * 32; e += T8_THREADS) {
+        const int d = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        if (c > r || (d * 32 + c == nv && d * 32 + r < nv)) Lb[lblk8_index(d, d) * T8_LBLK + r * T8_B + c] = 0.0;   // (pair spill-over at nv)
+    }
+    for (int e = tid; e < T8_NB8 * 64; e += T8_THREADS) {
+        const int blk = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        if (c > r) W8[(blk * 8 + r) * T8_WS + c] = 0.0;
+    }
+    __syncthreads();
+    if (warp >= T8_ROWS / 8) return;              // (the border warp of the panel solve has no role here)
+
+    const int rb = half * (T8_ROWS / 8) + warp;   // this warp's identity rows 8 rb .. 8 rb + 7
+    double acc[T8_NB8][2];
+#pragma unroll
+    for (int b8 = 0; b8 < T8_NB8; ++b8) {
+        acc[b8][0] = (b8 == rb && 2 * fk == fr) ? 1.0 : 0.0;
+        acc[b8][1] = (b8 == rb && 2 * fk + 1 == fr) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int b8 = 0; b8 < T8_NB8; ++b8) {
+        // W[c][r] = Y[r][c]:  c = 8 b8 + 2 fk (+1),  r = 8 rb + fr
+        double *out = Wi + (size_t)(b8 * 8 + 2 * fk) * NB + rb * 8 + fr;
+        if (b8 < rb) { out[0] = 0.0; out[NB] = 0.0; continue; }      // Y is upper triangular: W has zeros above its diagonal
+        const int sb = b8 >> 2, q = b8 & 3;
+        const double2 w = *reinterpret_cast<const double2 *>(W8 + (b8 * 8 + fr) * T8_WS + 2 * fk);
+        const double2 l = *reinterpret_cast<const double2 *>(Lb + lblk8_index(sb, sb) * T8_LBLK + (q * 8 + fr) * T8_B + q * 8 + 2 * fk);
+        double x0 = 0.0, x1 = 0.0;
+        dmma884_8(x0, x1, acc[b8][0], w.x);
+        dmma884_8(x0, x1, acc[b8][1], w.y);
+        double r0 = acc[b8][0], r1 = acc[b8][1];
+        dmma884_8(r0, r1, -x0, l.x);
+        dmma884_8(r0, r1, -x1, l.y);
+        dmma884_8(x0, x1, r0, w.x);
+        dmma884_8(x0, x1, r1, w.y);
+        const double nx0 = -x0, nx1 = -x1;
+#pragma unroll
+        for (int bp = b8 + 1; bp < T8_NB8; ++bp) {
+            const double2 lp = *reinterpret_cast<const double2 *>(Lb + lblk8_index(bp >> 2, sb) * T8_LBLK + ((bp & 3) * 8 + fr) * T8_B + q * 8 + 2 * fk);
+            dmma884_8(acc[bp][0], acc[bp][1], nx0, lp.x);
+            dmma884_8(acc[bp][0], acc[bp][1], nx1, lp.y);
+        }
+        if (b8 > rb) { out[0] = x0; out[NB] = x1; }                  // the diagonal 8x8 blocks stay as the factor kernel wrote them
+    }
+}
+
+int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, cudaStream_t s)
+{
+    if (B <= 0 || n <= 0) return 0;
+    if (A.ld & 1) { set_error("inv_blocks: ld=%d must be even", A.ld); return GPMC_EALIGN; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPMC_CUDA_CHECK(cudaFuncSetAttribute(inv_blocks8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
+        attr_set = true;
+    }
+    const int nt = (n + NB - 1) / NB;
+    dim3 grid(2 * nt, B);
+    prof_begin(KC_INV, s);
+    inv_blocks8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n, W, strideW);
+    prof_end(KC_INV, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s)
 {
     int rows = n_rows - j0 - NB;

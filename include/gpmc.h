@@ -180,7 +180,8 @@ int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ld
 
 /* Kernel tuning knobs for experiments.
  * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default).
- * key 1: panel factor kernel (0 auto, 1 always the full-inverse kernel, 2 the diagonal-inverse kernel whenever legal).
+ * key 1: panel factor kernel (0 = the diagonal-inverse kernel whenever the block inverse is not needed, 1 = always the
+ *        full-inverse kernel).
  * key 2: look-ahead in the blocked Cholesky (panel kernels overlapped with the update GEMM on side streams):
  *        0 auto (on when at most #SMs/2 matrices are in flight), 1 off, 2 on.
  * key 3: window (columns, multiple of 128) of the windowed schedule used for few large matrices; 0 = default.
