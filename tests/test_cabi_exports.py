@@ -26,6 +26,30 @@ def test_header_symbols_are_exported(gp):
     assert lib.gpmc_version() == 100
 
 
+def test_header_is_plain_c_and_links_against_the_library(gp, tmp_path):
+    """include/gpmc.h must be consumable by a C compiler (no C++-isms, no torch types), and a C program that calls the
+    host-only entry points must link against libgpmc.so and run without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    lib_dir = os.path.join(ROOT, 'gaussianprocess-mcmc_b200')
+    src = tmp_path / 'abi.c'
+    src.write_text(
+        '#include <stdio.h>\n#include "gpmc.h"\n'
+        'int main(void) {\n'
+        '  size_t w = gpmc_workspace_bytes(GPMC_OP_LOGLIK, 4096, 1, 8);\n'
+        '  printf("%d %d %zu %zu\\n", gpmc_version(), gpmc_panel_width(), w, gpmc_sds_workspace_bytes(512, 3, 4));\n'
+        '  return gpmc_set_tuning(99, 0) == GPMC_EINVAL ? 0 : 1;\n}\n')
+    exe = tmp_path / 'abi'
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                    '-L', lib_dir, '-lgpmc', '-Wl,-rpath,' + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == '100' and out[1] == '128'
+    assert int(out[2]) > 8 * 4096 * 4096 and int(out[3]) > 0
+
+
 def test_workspace_query_is_pure_host(gp):
     lib = gp._lib.load()
     one = lib.gpmc_workspace_bytes(gp._lib.OP_LOGLIK, 4096, 1, 1)
