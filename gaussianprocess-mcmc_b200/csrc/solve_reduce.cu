@@ -28,8 +28,8 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
-solve_reduce_kernel(BatchView L, int n, const double *__restrict__ va, const double *__restrict__ vb, int ldv,
-                    double *__restrict__ zout, double *__restrict__ loglik, const int *__restrict__ info)
+solve_reduce_kernel(BatchView L, int n, const double *va, const double *__restrict__ vb, int ldv,
+                    double *zout, double *__restrict__ loglik, const int *__restrict__ info)     // zout may alias va (in place)
 {
     extern __shared__ __align__(16) double sm[];
     const int npad = (n + SB - 1) / SB * SB;
@@ -139,7 +139,7 @@ solve_reduce_kernel(BatchView L, int n, const double *__restrict__ va, const dou
 // SM), so the same substitution is run RIGHT-LOOKING in launches: solve the 128x128 diagonal block (the kernel above
 // on a sub-view), then every row below subtracts its 128-column contribution in parallel over the whole chip.
 __global__ void __launch_bounds__(256)
-gemv_sub_kernel(BatchView L, int n, int j0, const double *__restrict__ z, double *__restrict__ w, int ldv, const int *__restrict__ info)
+gemv_sub_kernel(BatchView L, int n, int j0, const double *z, double *w, int ldv, const int *__restrict__ info)   // w aliases z (other rows)
 {
     const int b = blockIdx.y;
     if (L.count && b >= *L.count) return;
