@@ -326,9 +326,10 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
     SweepBuffers w;
     layout(w, (char *)ws_dev, N, P, cap);
     // pad columns of the matrices must be zero (the DMMA kernels contract over multiples of 16)
+    // (every slot has N + 1 rows -- the border row included -- and the slots are contiguous)
     if (w.ld != N) {
-        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)N * cap, s));
-        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)N * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
     }
     AuxCtx ctx{x_dev, N, D, P, n_ell, &w, s, jitter_policy};
     std::vector<int> active;

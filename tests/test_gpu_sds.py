@@ -291,6 +291,47 @@ def test_full_size_sweep_is_independent_of_batching(gp):
         assert np.abs(Fc[0] - Fa[c]).max() < 5e-2
 
 
+def test_results_do_not_depend_on_what_the_workspace_held_before(gp):
+    """The workspace is caller-owned scratch and reused across calls: whatever it held before (here: NaN everywhere)
+    must not leak into a result.  N is not a multiple of 16 on purpose: the pad columns of every matrix row -- border
+    rows and the last rows of the last slot included -- are read by the K-tails of the DMMA kernels."""
+    import torch
+    from gpmc_b200 import ops
+    n, B = 200, 6
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array(gp.synthetic.SCALE)
+    G, Hl = gp.synthetic.loglik_batch(B, n)
+
+    def poison(value):
+        buf = ops._default_ws.buf
+        assert buf is not None
+        buf[: buf.numel() // 8 * 8].view(torch.float64).fill_(value)
+        torch.cuda.synchronize()
+
+    def run():
+        F = torch.tensor(F0.copy()).cuda(); H = torch.tensor(H0.copy()).cuda()
+        out = []
+        for it in range(2):
+            nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it, seed=5)
+            out.append((nt.cpu().numpy(), ll.cpu().numpy(), st.cpu().numpy()))
+        ll2, info = ops.loglik_batched(torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(Hl).cuda())
+        return F.cpu().numpy(), H.cpu().numpy(), out, ll2.cpu().numpy(), info.cpu().numpy()
+
+    run()                                   # sizes the workspace
+    poison(0.0)
+    Fa, Ha, oa, la, ia = run()
+    poison(float('nan'))
+    Fb, Hb, ob, lb, ib = run()
+    assert np.all(ia == 0) and np.array_equal(ia, ib)
+    assert np.array_equal(la, lb)
+    for (ta, lla, sa), (tb, llb, sb) in zip(oa, ob):
+        assert np.all(sa == 0) and np.array_equal(sa, sb)
+        assert np.array_equal(ta, tb) and np.array_equal(lla, llb)
+    assert np.array_equal(Ha, Hb) and np.array_equal(Fa, Fb)
+    assert np.all(np.isfinite(Fb)) and np.all(np.isfinite(lb))
+
+
 def test_sweep_survives_numerically_singular_states(gp, capfd):
     """Chains whose K+S is numerically singular (noise ~1e-9, long length-scale) exercise the pyGPs jitter ladder
     inside the sweep (sliceSample.py:196,205 via jitchol): the sweep must finish, report a status per chain, never
