@@ -316,13 +316,22 @@ def test_results_do_not_depend_on_what_the_workspace_held_before(gp):
             nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it, seed=5)
             out.append((nt.cpu().numpy(), ll.cpu().numpy(), st.cpu().numpy()))
         ll2, info = ops.loglik_batched(torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(Hl).cuda())
-        return F.cpu().numpy(), H.cpu().numpy(), out, ll2.cpu().numpy(), info.cpu().numpy()
+        # the single-matrix auxiliary model and the jitchol Cholesky share the same scratch
+        K = ops.cov_assemble(x, Hl[:1])[0, :, :n].contiguous()
+        Sd = np.full(n, float(Hl[0, 2]) ** 2)
+        L, m, C, inf2 = ops.aux_var_model_device(K, Sd, G[0])
+        A = ops.cov_assemble(x, Hl, add_S=True)
+        inf3 = ops.potrf_batched(A, n=n, jitter_policy=gp.JITTER_PYGPS)
+        extra = [L.cpu().numpy(), m.cpu().numpy(), C.cpu().numpy(), inf2.cpu().numpy(), A.cpu().numpy()[:, :, :n], inf3.cpu().numpy()]
+        return F.cpu().numpy(), H.cpu().numpy(), out, ll2.cpu().numpy(), info.cpu().numpy(), extra
 
     run()                                   # sizes the workspace
     poison(0.0)
-    Fa, Ha, oa, la, ia = run()
+    Fa, Ha, oa, la, ia, xa = run()
     poison(float('nan'))
-    Fb, Hb, ob, lb, ib = run()
+    Fb, Hb, ob, lb, ib, xb = run()
+    for a, b in zip(xa, xb):
+        assert np.array_equal(np.tril(a) if a.ndim == 2 else a, np.tril(b) if b.ndim == 2 else b)
     assert np.all(ia == 0) and np.array_equal(ia, ib)
     assert np.array_equal(la, lb)
     for (ta, lla, sa), (tb, llb, sb) in zip(oa, ob):
