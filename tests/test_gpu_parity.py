@@ -89,6 +89,30 @@ def test_potrf_batched_matches_lapack(gp, so, n):
         np.testing.assert_allclose(np.log(np.diag(L[b])).sum(), np.log(np.diag(ref)).sum(), rtol=1e-12)
 
 
+@pytest.mark.parametrize('n,ld', [(300, 302), (129, 130), (257, 272), (1000, 1000), (455, 456)])
+def test_potrf_with_caller_leading_dimension_and_dirty_pads(gp, n, ld):
+    """gpmc_potrf_batched takes any even ld >= N; whatever sits in the pad columns (NaN here) and in the strict upper
+    triangle (garbage here) must not reach the factor (LAPACK dpotrf reads the lower triangle only)."""
+    import torch
+    import scipy.linalg
+    rs = np.random.RandomState(n)
+    B = 3
+    A = np.full((B, n, ld), np.nan)
+    ref = []
+    for b in range(B):
+        M = rs.standard_normal((n, n))
+        S = M @ M.T / n + (1.0 + b) * np.eye(n)
+        ref.append(scipy.linalg.cholesky(S, lower=True))
+        A[b, :, :n] = np.tril(S) + np.triu(rs.standard_normal((n, n)) * 1e3, 1)
+    T = torch.tensor(A, device='cuda')
+    info = gp.ops.potrf_batched(T, n=n, jitter_policy=gp.JITTER_NONE, zero_upper=True).cpu().numpy()
+    assert np.all(info == 0)
+    L = T.cpu().numpy()[:, :, :n]
+    for b in range(B):
+        assert np.all(np.triu(L[b], 1) == 0)
+        np.testing.assert_allclose(L[b], ref[b], rtol=0, atol=1e-12 * np.abs(ref[b]).max())
+
+
 def test_potrf_reports_lapack_info(gp):
     import torch
     import scipy.linalg
