@@ -119,7 +119,30 @@ static int mark_not_pd(const AuxCtx &c, int *info_dev, const std::vector<int> &i
     return 0;
 }
 
+// From a factored K+S (V1: L in the lower triangle, z in the border row up to its last block) to C = chol(R + 1e-11 I)
+// in V2, for the items of the views:
+static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitems)
+{
+    SweepBuffers &w = *c.w;
+    cudaStream_t s = c.s;
+    const long long strideW = (long long)w.nt * NB * NB;
+    int rc;
+    // ---- z = L^-1 g and the log marginal (:147)
+    if ((rc = border_finish(V1, w.n, w.G, w.info1, nitems, s))) return rc;
+    if ((rc = border_get(V1, w.n, w.z, w.ldv, w.info1, nitems, s))) return rc;
+    // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
+    if ((rc = inverse_sequence(V1, w.n, nitems, w.Wsave, strideW, s))) return rc;
+    if ((rc = launch_trmv(V1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, nitems, s))) return rc;
+    if ((rc = r_sequence(V2, V1, w.n, nitems, w.svec, w.ldv, s))) return rc;
+    // ---- C = chol(R + 1e-11 I) (jitchol, :205)
+    if ((rc = fill_int_mapped(w.info2, 0, V1.map, V1.count, nitems, s))) return rc;
+    return potrf_sequence(V2, w.n, nitems, w.info2, w.Wtmp, NB * NB, 0, 0, s);
+}
+
 // Evaluate the auxiliary model at w.theta for the chains listed in `active` (w.map/w.count hold the same list).
+// The factorisations are run optimistically: chol(K+S), everything that follows from it, and chol(R + 1e-11 I) are
+// queued without looking at info[], then BOTH status vectors are read in one host synchronisation; only when a
+// factorisation failed (rare) does the pyGPs jitter ladder run, for the failed chains alone.
 static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
 {
     SweepBuffers &w = *c.w;
@@ -131,106 +154,113 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     BatchView A2{w.buf2, mat, w.ld, w.map, w.count};
     const long long strideW = (long long)w.nt * NB * NB;
     int rc;
-    // ---- K+S and its Cholesky factor (jitchol, :196)
+    // ---- K+S and its Cholesky factor (jitchol, :196); g rides through the factorisation as a border row:
+    //      z = L^-1 g comes out of the update GEMMs and panel solves
     if ((rc = fill_int_mapped(w.info1, 0, w.map, w.count, na, s))) return rc;
     if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A1, na, s))) return rc;
-    // g rides through the factorisation as a border row: z = L^-1 g comes out of the update GEMMs and panel solves
     if ((rc = border_set(A1, w.n, w.g, w.ldv, na, s))) return rc;
     if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
-    if (c.jitter_policy == GPMC_JITTER_PYGPS) {
-        std::vector<int> failed, info;
-        if ((rc = failed_items(c, w.info1, active, failed, info))) return rc;
-        if (!failed.empty()) {
-            if (debug_on()) fprintf(stderr, "[gpmc] chol(K+S) failed for %zu of %d chains (first: chain %d, info %d): jitter ladder\n",
-                                    failed.size(), na, failed[0], info[failed[0]]);
-            std::vector<double> th((size_t)w.cap * c.P), jit(w.cap, 0.0);
-            GPMC_CUDA_CHECK(cudaMemcpyAsync(th.data(), w.theta, th.size() * 8, cudaMemcpyDeviceToHost, s));
-            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-            std::vector<int> todo, hopeless;
-            for (int id : failed) {
-                const double dv = host_diag_value(&th[(size_t)id * c.P], c.P);
-                if (dv <= 0.0) hopeless.push_back(id);              // any(diag <= 0): LinAlgError
-                else { jit[id] = dv * 1e-6; todo.push_back(id); }   // (NaN diag lands here and keeps failing)
-            }
-            int *cnt = w.count + 16;         // scratch count next to the main one (same 256-byte slot)
-            for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
-                const int nf = (int)todo.size();
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
-                BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
-                if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
-                if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, w.jit, F1, nf, s))) return rc;
-                if ((rc = border_set(F1, w.n, w.g, w.ldv, nf, s))) return rc;
-                if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
-                std::vector<int> still, info2;
-                if ((rc = failed_items(c, w.info1, todo, still, info2))) return rc;
-                for (int id : still) jit[id] *= 10.0;
-                todo.swap(still);
-            }
-            // "not positive definite, even with jitter"
-            hopeless.insert(hopeless.end(), todo.begin(), todo.end());
-            if ((rc = mark_not_pd(c, w.info1, hopeless))) return rc;
-        }
+    if ((rc = aux_downstream(c, A1, A2, na))) return rc;
+    if (c.jitter_policy != GPMC_JITTER_PYGPS) return 0;
+
+    // ---- one synchronisation: status of both factorisations
+    std::vector<int> info1(w.cap), info2(w.cap);
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info1.data(), w.info1, w.cap * sizeof(int), cudaMemcpyDeviceToHost, s));
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info2.data(), w.info2, w.cap * sizeof(int), cudaMemcpyDeviceToHost, s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<int> failed1, failed2;
+    for (int id : active) {
+        if (info1[id] != 0) failed1.push_back(id);
+        else if (info2[id] != 0) failed2.push_back(id);
     }
-    // ---- z = L^-1 g and the log marginal (:147)
-    if ((rc = border_finish(A1, w.n, w.G, w.info1, na, s))) return rc;
-    if ((rc = border_get(A1, w.n, w.z, w.ldv, w.info1, na, s))) return rc;
-    // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
-    if ((rc = inverse_sequence(A1, w.n, na, w.Wsave, strideW, s))) return rc;
-    if ((rc = launch_trmv(A1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, na, s))) return rc;
-    if ((rc = r_sequence(A2, A1, w.n, na, w.svec, w.ldv, s))) return rc;
-    // ---- C = chol(R + 1e-11 I) (jitchol, :205)
-    if ((rc = fill_int_mapped(w.info2, 0, w.map, w.count, na, s))) return rc;
-    if ((rc = potrf_sequence(A2, w.n, na, w.info2, w.Wtmp, NB * NB, 0, 0, s))) return rc;
-    if (c.jitter_policy == GPMC_JITTER_PYGPS) {
-        std::vector<int> failed, info;
-        if ((rc = failed_items(c, w.info2, active, failed, info))) return rc;
-        // chains whose K+S already failed carry NaN everywhere: nothing to retry
-        std::vector<int> info1;
-        if (!failed.empty()) {
-            info1.resize(w.cap);
-            GPMC_CUDA_CHECK(cudaMemcpyAsync(info1.data(), w.info1, w.cap * 4, cudaMemcpyDeviceToHost, s));
-            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-            std::vector<int> todo;
-            for (int id : failed) if (info1[id] == 0) todo.push_back(id);
-            if (debug_on()) fprintf(stderr, "[gpmc] chol(R+1e-11 I) failed for %zu of %d chains (first: chain %d, info %d): jitter ladder on %zu\n",
-                                    failed.size(), na, failed[0], info[failed[0]], todo.size());
-            int *cnt = w.count + 16;
-            std::vector<double> jit(w.cap, 0.0), mean(w.cap, 0.0);
-            std::vector<int> bad(w.cap, 0);
-            bool first = true;
-            for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
-                const int nf = (int)todo.size();
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
-                BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
-                BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
-                if ((rc = r_sequence(F2, F1, w.n, nf, w.svec, w.ldv, s))) return rc;      // rebuild R + 1e-11 I
-                if (first) {
-                    if ((rc = diag_stats(F2, w.n, w.mean, w.bad, nf, s))) return rc;
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), w.mean, w.cap * 8, cudaMemcpyDeviceToHost, s));
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(bad.data(), w.bad, w.cap * 4, cudaMemcpyDeviceToHost, s));
-                    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-                    std::vector<int> keep;
-                    for (int id : todo) { if (!bad[id]) { jit[id] = mean[id] * 1e-6; keep.push_back(id); } }
-                    first = false;
-                    if (keep.size() != todo.size()) { todo.swap(keep); --attempt; continue; }
-                }
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
-                if ((rc = add_diag(F2, w.n, w.jit, nf, s))) return rc;
-                if ((rc = fill_int_mapped(w.info2, 0, w.fmap, cnt, nf, s))) return rc;
-                if ((rc = potrf_sequence(F2, w.n, nf, w.info2, w.Wtmp, NB * NB, 0, 0, s))) return rc;
-                std::vector<int> still, tmp;
-                if ((rc = failed_items(c, w.info2, todo, still, tmp))) return rc;
-                for (int id : still) jit[id] *= 10.0;
-                todo.swap(still);
-            }
-            if ((rc = mark_not_pd(c, w.info2, todo))) return rc;
+    if (failed1.empty() && failed2.empty()) return 0;
+    int *cnt = w.count + 16;             // scratch count next to the main one (same 256-byte slot)
+
+    if (!failed1.empty()) {
+        if (debug_on()) fprintf(stderr, "[gpmc] chol(K+S) failed for %zu of %d chains (first: chain %d, info %d): jitter ladder\n",
+                                failed1.size(), na, failed1[0], info1[failed1[0]]);
+        std::vector<double> th((size_t)w.cap * c.P), jit(w.cap, 0.0);
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(th.data(), w.theta, th.size() * 8, cudaMemcpyDeviceToHost, s));
+        GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<int> todo, hopeless, recovered;
+        for (int id : failed1) {
+            const double dv = host_diag_value(&th[(size_t)id * c.P], c.P);
+            if (dv <= 0.0) hopeless.push_back(id);              // any(diag <= 0): LinAlgError
+            else { jit[id] = dv * 1e-6; todo.push_back(id); }   // (NaN diag lands here and keeps failing)
         }
+        for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
+            const int nf = (int)todo.size();
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
+            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
+            if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, w.jit, F1, nf, s))) return rc;
+            if ((rc = border_set(F1, w.n, w.g, w.ldv, nf, s))) return rc;
+            if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
+            std::vector<int> still, tmp;
+            if ((rc = failed_items(c, w.info1, todo, still, tmp))) return rc;
+            for (int id : todo) if (tmp[id] == 0) recovered.push_back(id);
+            for (int id : still) jit[id] *= 10.0;
+            todo.swap(still);
+        }
+        // "not positive definite, even with jitter"
+        hopeless.insert(hopeless.end(), todo.begin(), todo.end());
+        if ((rc = mark_not_pd(c, w.info1, hopeless))) return rc;
+        // the chains the ladder rescued: everything downstream of chol(K+S) again, for them alone
+        if (!recovered.empty()) {
+            const int nr = (int)recovered.size();
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, recovered.data(), nr * 4, cudaMemcpyHostToDevice, s));
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nr, 4, cudaMemcpyHostToDevice, s));
+            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
+            if ((rc = aux_downstream(c, F1, F2, nr))) return rc;
+            std::vector<int> bad2, tmp;
+            if ((rc = failed_items(c, w.info2, recovered, bad2, tmp))) return rc;
+            failed2.insert(failed2.end(), bad2.begin(), bad2.end());
+        }
+        // chains whose K+S stayed unfactorable carry NaN everywhere (and a nonzero info2 from the optimistic pass): they
+        // are rejected proposals, nothing to retry
+    }
+
+    if (!failed2.empty()) {
+        std::vector<int> todo = failed2;
+        if (debug_on()) fprintf(stderr, "[gpmc] chol(R+1e-11 I) failed for %zu of %d chains (first: chain %d): jitter ladder\n",
+                                todo.size(), na, todo[0]);
+        std::vector<double> jit(w.cap, 0.0), mean(w.cap, 0.0);
+        std::vector<int> bad(w.cap, 0);
+        bool first = true;
+        for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
+            const int nf = (int)todo.size();
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
+            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
+            if ((rc = r_sequence(F2, F1, w.n, nf, w.svec, w.ldv, s))) return rc;      // rebuild R + 1e-11 I
+            if (first) {
+                if ((rc = diag_stats(F2, w.n, w.mean, w.bad, nf, s))) return rc;
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), w.mean, w.cap * 8, cudaMemcpyDeviceToHost, s));
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(bad.data(), w.bad, w.cap * 4, cudaMemcpyDeviceToHost, s));
+                GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+                std::vector<int> keep;
+                for (int id : todo) { if (!bad[id]) { jit[id] = mean[id] * 1e-6; keep.push_back(id); } }
+                first = false;
+                if (keep.size() != todo.size()) { todo.swap(keep); --attempt; continue; }
+            }
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
+            if ((rc = add_diag(F2, w.n, w.jit, nf, s))) return rc;
+            if ((rc = fill_int_mapped(w.info2, 0, w.fmap, cnt, nf, s))) return rc;
+            if ((rc = potrf_sequence(F2, w.n, nf, w.info2, w.Wtmp, NB * NB, 0, 0, s))) return rc;
+            std::vector<int> still, tmp;
+            if ((rc = failed_items(c, w.info2, todo, still, tmp))) return rc;
+            for (int id : still) jit[id] *= 10.0;
+            todo.swap(still);
+        }
+        if ((rc = mark_not_pd(c, w.info2, todo))) return rc;
     }
     return 0;
 }
+
 
 }  // namespace gpmc
 
