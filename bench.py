@@ -11,6 +11,10 @@ per-chain results are all-gathered once (the "one all-gather of samples per swee
 
 Prints ONE JSON line (rank 0).  `value` is timed with the inputs resident in HBM; `e2e` goes through
 the C-ABI host-buffer call (pinned H2D of x/g/theta and D2H of loglik/info inside the timed region).
+Besides the headline (BASELINE config 5 shard) the line carries `configs`: one sub-record per other
+BASELINE config shape (log-lik unit at C2/C3/C4) and per device-resident SDS sweep (whole
+`surrogate_slice_sampling` transitions, sliceSample.py:76-163, at C2, C3 and a C5 shard), each with
+its own timing, roofline fraction and a GPU-vs-oracle check on sampled items.
 """
 import argparse
 import json
@@ -19,14 +23,10 @@ import sys
 import threading
 import time
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# ncu-measured DRAM bytes per eval of the update kernel, keyed by (N, panel width); see profiles/
-TRAFFIC_BYTES_PER_EVAL = {(4096, 128): 827.98e6}
 METRIC = 'GP log-lik evals/sec (N=4096, batched chains)'
 UNIT = 'evals/s'
 
@@ -43,16 +43,20 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-peaks', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the sub-records of the other BASELINE configs / SDS sweeps')
+    ap.add_argument('--only-configs', default=None, help='comma list of sub-record names to run (e.g. C3_loglik,C3_sds)')
     ap.add_argument('--gemm-cfg', type=int, default=None, help='experiment: DMMA tile kernel variant (0: 8 warps, 1: 16 warps)')
     return ap.parse_args()
 
 
 def workload_config(n, B, world):
-    """`config` of the JSON line: identical for the CUDA arm and the reference arm."""
+    """`config` of the JSON line: IDENTICAL (keys and values) for the CUDA arm and the reference arm."""
     return {'workload': 'BASELINE config 5 (8xB200 chain-parallel: N=4096, 8192 chains sharded by GPU): N=%d, %d chains '
                         'per GPU, one log-lik eval per chain per step, SE+noise kernel on a unit-spaced 1-D grid '
                         '(IH45-shaped)' % (n, B),
-            'n': n, 'chains_per_gpu': B, 'evals_per_step': world * B, 'kernel': 'SE iso + noise'}
+            'n': n, 'chains_per_gpu': B, 'evals_per_step': world * B, 'kernel': 'SE iso + noise',
+            'l2': 'per-step working set %d matrices x %.0f MiB >> 126 MB L2 (no flush needed)' % (B, n * n * 8 / 2 ** 20),
+            'collective': 'one all_gather of loglik per step' if world > 1 else 'none (single rank)'}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -102,6 +106,7 @@ class ClockSampler(threading.Thread):
             self._stop_evt.wait(0.2)
 
     def stop(self):
+        import numpy as np
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
@@ -110,12 +115,41 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------ CPU (oracle)
-def cpu_unit_evals_per_s(n, sample, form):
+def set_blas_threads():
+    """The CPU arm uses every host core.  torchrun exports OMP_NUM_THREADS=1 when nproc > 1, which numpy's OpenBLAS
+    honours, so the thread count is set explicitly BEFORE numpy is imported and the EFFECTIVE count is what gets
+    reported (threadpoolctl)."""
+    cores = os.cpu_count() or 1
+    for k in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = str(cores)
+    return cores
+
+
+def effective_blas_threads():
+    try:
+        import threadpoolctl
+        import numpy  # noqa: F401  (loads the BLAS so that threadpoolctl can see it)
+        import scipy.linalg  # noqa: F401
+        pools = [p for p in threadpoolctl.threadpool_info() if p.get('user_api') == 'blas']
+        if pools:
+            return int(max(p.get('num_threads', 1) for p in pools))
+    except Exception:
+        pass
+    return int(os.environ.get('OPENBLAS_NUM_THREADS', os.cpu_count() or 1))
+
+
+def cpu_unit_evals_per_s(n, sample, form, ard=0, first=0):
     """Time the oracle's restatement of the unit on the host cores (OpenBLAS threads = all cores)."""
+    import numpy as np
     from oracle import sds_oracle as so
     import gpmc_b200 as gp
-    x = np.arange(n, dtype=np.float64).reshape(n, 1)
-    G, H = gp.synthetic.loglik_batch(sample, n)
+    if ard:
+        x, _ = gp.synthetic.ard_inputs(n, ard)
+        n_ell = ard
+    else:
+        x = np.arange(n, dtype=np.float64).reshape(n, 1)
+        n_ell = 1
+    G, H = gp.synthetic.loglik_batch(sample, n, n_ell=n_ell, first_chain=first)
     so.loglik_unit(x[:256], G[0, :256], H[0], form=form)        # warm the BLAS threads
     t0 = time.perf_counter()
     vals = [so.loglik_unit(x, G[i], H[i], form=form) for i in range(sample)]
@@ -129,7 +163,7 @@ def run_reference(args, rank, world):
     in the form the reference writes it: dense inv for the quadratic form (sliceSample.py:147)."""
     if rank != 0:
         return
-    cores = os.cpu_count()
+    threads = effective_blas_threads()
     sample = max(1, min(2, 12 // max(1, args.steps)))      # ~5 s per eval at N=4096 on 8 cores
     for _ in range(min(args.warmup, 1)):
         cpu_unit_evals_per_s(args.n, 1, 'inv')
@@ -144,13 +178,14 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(args.n, args.chains_per_gpu, max(1, args.gpus)),
-                       reference_sample='each timed step is a bounded sample of that workload: %d evals, one chain after '
-                                        'another on the host (the reference has no multi-chain mode, framework.py:68-75), '
-                                        'in the form the reference writes: sliceSample.py:136-137,183-190,196,147 '
-                                        '(dense inv)' % sample),
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d steps x %d evals at N=%d, numpy/scipy OpenBLAS on %d threads' % (args.steps, sample, args.n, cores)},
+        'config': workload_config(args.n, args.chains_per_gpu, max(1, args.gpus)),
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'host_cpus': os.cpu_count(),
+                         'sample': 'each timed step is a bounded sample of the workload: %d steps x %d evals at N=%d, one '
+                                   'chain after another on the host (the reference has no multi-chain mode, '
+                                   'framework.py:68-75), in the form the reference writes: sliceSample.py:136-137,183-190,'
+                                   '196,147 (dense inv); numpy/scipy OpenBLAS, %d threads in effect (threadpoolctl; set '
+                                   'explicitly, torchrun\'s OMP_NUM_THREADS=1 overridden)' % (args.steps, sample, args.n, threads)},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -185,7 +220,171 @@ def measured_peaks(torch, gp):
     return out
 
 
+def committed_traffic(n, nb):
+    """DRAM bytes per eval of the update kernel from the committed ncu summary of the CURRENT kernel
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` capture); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        for row in d.get('update_kernel', []):
+            if row.get('n') == n and row.get('panel_width') == nb:
+                return row.get('dram_bytes_per_eval'), d.get('source')
+    except Exception:
+        pass
+    return None, None
+
+
+def hbm_peak_gbs():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs'), 'MEASURED_PEAKS.json'
+    except Exception:
+        return 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+
+
+def chol_kernel_ms(prof):
+    return prof['gemm_update'][0] + prof['potf2'][0] + prof['panel_trsm'][0] + prof.get('fused_small', (0.0, 0))[0]
+
+
+def sub_loglik(gp, torch, np, name, n, B, ard, reps, peak_tf, n_check, what):
+    """Log-lik unit at one BASELINE config shape: timing (CUDA events), Cholesky roofline fraction (N^3/3 flop per eval
+    over the wall time of the pass AND over the Cholesky launches alone), GPU vs oracle on `n_check` sampled items."""
+    from oracle import sds_oracle as so
+    if ard:
+        x, _ = gp.synthetic.ard_inputs(n, ard)
+        n_ell = ard
+    else:
+        x = np.arange(n, dtype=np.float64).reshape(n, 1)
+        n_ell = 1
+    G, H = gp.synthetic.loglik_batch(B, n, n_ell=n_ell)
+    xd, Gd, Hd = torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(H).cuda()
+    for _ in range(3):
+        ll, info = gp.ops.loglik_batched(xd, Gd, Hd)
+    torch.cuda.synchronize()
+    gp.ops.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ll, info = gp.ops.loglik_batched(xd, Gd, Hd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    prof = gp.ops.profile_read()
+    gp.ops.profile(False)
+    launches = int(sum(v[1] for v in prof.values()))
+    flops = B * n ** 3 / 3.0
+    ll_h = ll.cpu().numpy()
+    idx = np.unique(np.linspace(0, B - 1, min(B, n_check)).astype(int))
+    t0 = time.perf_counter()
+    ref = np.array([so.loglik_unit(x, G[i], H[i], form='chol') for i in idx])
+    cpu_dt = time.perf_counter() - t0
+    rel = float(np.max(np.abs(ll_h[idx] - ref) / np.abs(ref)))
+    tf_pass = flops / (ms * 1e-3) / 1e12
+    rec = {'name': name, 'kind': 'loglik', 'workload': what, 'n': n, 'batch': B, 'ard_dims': ard, 'reps': reps,
+           'ms_per_pass': ms, 'evals_per_s': B / (ms * 1e-3), 'failed_items': int((info != 0).sum().item()),
+           'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'flop_per_eval': n ** 3 / 3.0,
+                        'achieved': tf_pass, 'peak': peak_tf, 'frac': tf_pass / peak_tf if peak_tf else None,
+                        'what': 'N^3/3 flop per eval over the WALL time of the whole pass (assembly, reductions, launch gaps included)'},
+           'kernel_ms': {k: round(v[0] / reps, 4) for k, v in prof.items() if v[0] > 0},
+           'gpu_launches_per_pass': launches // max(1, reps),
+           'gpu_vs_oracle_max_rel_err': rel, 'oracle_items': [int(i) for i in idx],
+           'cpu_oracle_s_per_eval': cpu_dt / len(idx)}
+    del xd, Gd, Hd
+    return rec
+
+
+def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check, what, dist=None, world=1, rank=0):
+    """Device-resident SDS sweeps (whole surrogate_slice_sampling transitions for B chains PER RANK through
+    ChainEnsemble): chain-sweeps/s, trips, 4/3 N^3 flop per auxiliary-model evaluation against the DGEMM rate,
+    per-rank busy time (trip-count imbalance) and a tape-driven comparison with the oracle on sampled chains."""
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    if ard:
+        x, y = gp.synthetic.ard_inputs(n, ard)
+        n_ell = ard
+    else:
+        x, y = gp.synthetic.ih45_series(n)
+        n_ell = 1
+    P = n_ell + 2
+    scale = np.array([gp.synthetic.SCALE[0]] * n_ell + list(gp.synthetic.SCALE[1:]))
+    F0, H0 = gp.synthetic.chain_states(B, n, n_ell=n_ell, first_chain=rank * B)
+    ens = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=1, max_trips=64, sharded_input=True,
+                                  distributed=(world > 1))
+    ens.sweep(start_iter)                                   # warm-up: allocations, lazy module load, NCCL
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    gp.ops.profile(True)
+    busy, trips = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(sweeps):
+        Hg, llg, ntg = ens.sweep(start_iter + 1 + i)        # gathered over ranks
+        busy.append(ens.last_busy_ms)
+        trips.append(ntg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = gp.ops.profile_read()
+    gp.ops.profile(False)
+    busy_local = float(np.sum(busy))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tb = torch.zeros(world, dtype=torch.float64, device='cuda')
+        tb[rank] = busy_local
+        dist.all_reduce(tb)
+        busy_ranks = [float(v) for v in tb.cpu().tolist()]
+    else:
+        busy_ranks = [busy_local]
+    trips = np.stack(trips)                                 # [sweeps, world*B]
+    evals = int((trips + 1).sum())                          # aux-model evaluations: one at theta + one per trip
+    flops = evals * (4.0 / 3.0) * n ** 3
+    tf = flops / (ms * 1e-3) / 1e12
+    rec = {'name': name, 'kind': 'sds_sweep', 'workload': what, 'n': n, 'chains_per_gpu': B, 'chains': world * B,
+           'ard_dims': ard, 'sweeps': sweeps, 'start_iter': start_iter + 1,
+           's_per_sweep': ms * 1e-3 / sweeps, 'chain_sweeps_per_s': world * B * sweeps / (ms * 1e-3),
+           'mean_trips': float(trips.mean()), 'max_trips': int(trips.max()), 'aux_evals': evals,
+           'exhausted_chains': int(ens.exhausted_total),
+           'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'flop_per_aux_eval': (4.0 / 3.0) * n ** 3,
+                        'achieved': tf, 'peak': peak_tf * world if peak_tf else None,
+                        'frac': tf / (peak_tf * world) if peak_tf else None,
+                        'what': '4/3 N^3 flop per auxiliary-model evaluation (chol(K+S), U = L^-T, R = S - S U U^T S, chol(R)) '
+                                'over the WALL time of the sweeps (control kernels, host round trips, idle tails included)'},
+           'busy_ms_per_rank': busy_ranks,
+           'imbalance_max_over_mean': (max(busy_ranks) / (sum(busy_ranks) / len(busy_ranks))) if min(busy_ranks) > 0 else None,
+           'kernel_ms_rank0': {k: round(v[0], 3) for k, v in prof.items() if v[0] > 0},
+           'gpu_launches_rank0': int(sum(v[1] for v in prof.values()))}
+    del ens
+    # ---- parity on sampled chains: tape-driven transition on the device vs the tape-driven oracle (reduced R form, the
+    # one the device evaluates): theta' and trip counts exact, log N(g) to 1e-10
+    if rank == 0 and n_check > 0:
+        F0c, H0c = gp.synthetic.chain_states(n_check, n, n_ell=n_ell, first_chain=7)
+        tapes = [Tape.from_seed(4242 + c, n, p=P, max_trips=64) for c in range(n_check)]
+        Fd = torch.tensor(F0c).cuda()
+        Hd = torch.tensor(H0c).cuda()
+        tp = gp.ops.Tape(np.stack([t.z for t in tapes]), np.stack([t.v for t in tapes]), [float(t.u0) for t in tapes],
+                         np.stack([t.U for t in tapes]))
+        nt, ll, st = gp.ops.sds_sweep(x, y, Fd, Hd, scale, start_iter, tape=tp)
+        nt, ll, Hn, Fn = nt.cpu().numpy(), ll.cpu().numpy(), Hd.cpu().numpy(), Fd.cpu().numpy()
+        worst_h = worst_ll = worst_f = 0.0
+        trips_equal = True
+        t0 = time.perf_counter()
+        for c in range(n_check):
+            tr = so.SweepTrace()
+            of, oh = so.surrogate_slice_sampling(F0c[c], x, y, H0c[c], scale, start_iter, tapes[c], trace=tr, r_form='reduced')
+            trips_equal = trips_equal and (int(nt[c]) == tr.n_trips)
+            worst_h = max(worst_h, float(np.max(np.abs(Hn[c] - oh) / np.abs(oh))))
+            worst_ll = max(worst_ll, abs(ll[c] - tr.propG[-1]) / abs(tr.propG[-1]))
+            worst_f = max(worst_f, float(np.abs(Fn[c] - of).max()))
+        rec['gpu_vs_oracle'] = {'chains': n_check, 'trips_equal': bool(trips_equal), 'theta_max_rel_err': worst_h,
+                                'loglik_max_rel_err': float(worst_ll), 'f_max_abs_err': worst_f,
+                                'cpu_oracle_s_per_transition': (time.perf_counter() - t0) / n_check,
+                                'how': 'tape-driven transition (explicit draws in the reference order) on the device vs oracle/sds_oracle.py'}
+    return rec
+
+
 def run_b200(args):
+    import numpy as np
     import torch
     import gpmc_b200 as gp
     rank = int(os.environ.get('RANK', '0'))
@@ -222,8 +421,14 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     peaks = {}
-    if rank == 0 and not args.no_peaks:
-        peaks = measured_peaks(torch, gp)
+    if not args.no_peaks:
+        if rank == 0:
+            peaks = measured_peaks(torch, gp)
+        if world > 1:                                      # every rank needs the DGEMM figure for its sub-records
+            t = torch.tensor([peaks.get('cublas_dgemm_8192_tflops', 0.0)], dtype=torch.float64, device='cuda')
+            dist.broadcast(t, 0)
+            if rank != 0:
+                peaks = {'cublas_dgemm_8192_tflops': float(t.item())}
 
     for _ in range(max(1, args.warmup)):                  # at least one: first-touch allocations, lazy module load
         ll, info = step()
@@ -269,6 +474,42 @@ def run_b200(args):
                'h2d_bytes_per_step': int(x_h.nbytes + G_h.nbytes + H_h.nbytes),
                'd2h_bytes_per_step': int(B * 8 + B * 4)}
         assert np.array_equal(ll_h, ll.cpu().numpy()), 'host-buffer path and device path disagree'
+    ll_first = ll.cpu().numpy()[:max(1, args.cpu_sample)].copy()
+    del G, H, gathered
+
+    # ---- sub-records: the other BASELINE configs and the device-resident SDS sweeps (every rank takes part in the
+    # SDS C5-shard record so that per-rank busy time and the 1->N curve of the real sampler are visible)
+    peak_tf = peaks.get('cublas_dgemm_8192_tflops')
+    configs = []
+    if not args.no_configs:
+        want = set(args.only_configs.split(',')) if args.only_configs else None
+
+        def on(name):
+            return want is None or name in want
+        try:
+            if world == 1:
+                if on('C2_loglik'):
+                    configs.append(sub_loglik(gp, torch, np, 'C2_loglik', 2048, 64, 0, 10, peak_tf, 8,
+                                              'BASELINE config 2: IH45-shaped series, N=2048, SE+noise, 64 chains, 1 B200'))
+                if on('C3_loglik'):
+                    configs.append(sub_loglik(gp, torch, np, 'C3_loglik', 512, 4096, 4, 5, peak_tf, 8,
+                                              'BASELINE config 3: N=512, 4096 chains, ARD kernel D=4'))
+                if on('C4_loglik'):
+                    configs.append(sub_loglik(gp, torch, np, 'C4_loglik', 16384, 1, 0, 3, peak_tf, 1,
+                                              'BASELINE config 4: single chain N=16384, blocked Cholesky per step'))
+                if on('C2_sds'):
+                    configs.append(sub_sds(gp, torch, np, 'C2_sds', 2048, 64, 0, 2, 0, peak_tf, 1,
+                                           'BASELINE config 2 shape, whole SDS transitions on the device'))
+                if on('C3_sds'):
+                    configs.append(sub_sds(gp, torch, np, 'C3_sds', 512, 4096, 4, 2, 0, peak_tf, 2,
+                                           'BASELINE config 3: fused on-device slice loop, N=512, 4096 chains, ARD D=4'))
+            if on('C5_sds'):
+                configs.append(sub_sds(gp, torch, np, 'C5_sds', n, 256, 0, 1, 0, peak_tf, 1 if world == 1 else 0,
+                                       'BASELINE config 5 shard of the real sampler: N=%d, 256 chains per GPU, whole SDS '
+                                       'transitions, chains sharded by GPU, one all-gather per sweep' % n,
+                                       dist=dist, world=world, rank=rank))
+        except Exception as e:                              # a sub-record must never cost the headline line
+            configs.append({'name': 'error', 'error': repr(e)})
 
     if rank != 0:
         if world > 1:
@@ -278,7 +519,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel family: the blocked Cholesky (DMMA update + panel kernels)
     evals_timed = B * args.steps
     chol_flops = n ** 3 / 3.0                                    # algorithmic flops per eval
-    chol_ms = prof['gemm_update'][0] + prof['potf2'][0] + prof['panel_trsm'][0]
+    chol_ms = chol_kernel_ms(prof)
     gemm_ms, gemm_launches = prof['gemm_update']
     achieved = evals_timed * chol_flops / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None
     # executed MACs of the update kernel: full 128-row tiles of every block column
@@ -288,41 +529,43 @@ def run_b200(args):
     # the 16 32x32 sub-tiles of the diagonal block (6 skipped, 4 at 10/16), one 8-row fragment for the border row
     exec_flops = sum(2.0 * (j * nb) * nb * (((n - j * nb - nb + 127) // 128 * 128) + 0.53125 * nb + 8) for j in range(1, nt))
     peak = peaks.get('cublas_dgemm_8192_tflops')
+    traffic, traffic_src = committed_traffic(n, nb)
+    hbm_peak, hbm_src = hbm_peak_gbs()
     roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
         'frac': (achieved / peak) if (achieved and peak) else None,
-        # DRAM bytes per eval of the dominant kernel (all update launches of one factorisation) from an ncu capture
-        # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/), next to the algorithmic bytes (every L row read
-        # once per block column + the block column read and written once)
-        'traffic': TRAFFIC_BYTES_PER_EVAL.get((n, nb)), 'traffic_unit': 'bytes per eval (update kernel)',
+        # DRAM bytes per eval of the dominant kernel (all update launches of one factorisation) from the committed ncu
+        # capture of the current kernel (dram__bytes_read.sum + dram__bytes_write.sum), next to the algorithmic bytes
+        # (every L row read once per block column + the block column read and written once)
+        'traffic': traffic, 'traffic_unit': 'bytes per eval (update kernel)', 'traffic_source': traffic_src,
         'traffic_algorithmic': sum((n - j * nb) * (j * nb) * 8 + 2 * (n - j * nb) * nb * 8 for j in range(1, nt)),
         'peak_source': 'measured in this run: cuBLAS DGEMM 8192^3 FP64 (MEASURED_PEAKS.json has no FP64 figure); '
                        'nominal B200 FP64 tensor 40 TFLOP/s',
         'what': 'batched blocked Cholesky (TMA-staged DMMA update kernel + potf2 + panel solve launches), N^3/3 flop per eval '
                 'over the summed CUDA-event durations of those launches on their stream',
         'frac_of_nominal_40tf': (achieved / 40.0) if achieved else None,
+        'whole_step': {'tflops': world * evals_timed * chol_flops / (ms * 1e-3) / 1e12 / world,
+                       'frac': (evals_timed * chol_flops / (ms * 1e-3) / 1e12 / peak) if peak else None,
+                       'what': 'N^3/3 flop per eval over the wall time of the step (assembly and reductions included), per GPU'},
         'update_kernel': {'ms_total': gemm_ms, 'launches': gemm_launches,
                           'executed_tflops': evals_timed * exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None},
         'kernel_ms': {k: v[0] for k, v in prof.items()},
         'assemble': {'bytes_per_eval': 8.0 * n * (n + 64) / 2, 'ms_total': prof['assemble'][0],
-                     'achieved_gbs': evals_timed * 8.0 * n * (n + 64) / 2 / (prof['assemble'][0] * 1e-3) / 1e9 if prof['assemble'][0] > 0 else None},
+                     'achieved_gbs': evals_timed * 8.0 * n * (n + 64) / 2 / (prof['assemble'][0] * 1e-3) / 1e9 if prof['assemble'][0] > 0 else None,
+                     'hbm_peak_gbs': hbm_peak, 'hbm_peak_source': hbm_src},
         'measured_fp64': peaks,
     }
-    try:
-        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        roofline['assemble']['hbm_peak_gbs'] = mp.get('hbm_gbs')
-    except Exception:
-        roofline['assemble']['hbm_peak_gbs'] = 6650.0
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # the CPU arm is reported at N=1 only
+        threads = effective_blas_threads()
         v_inv, dt_inv, vals = cpu_unit_evals_per_s(n, args.cpu_sample, 'inv')
         v_chol, dt_chol, vals_c = cpu_unit_evals_per_s(n, args.cpu_sample, 'trsv')
-        got = ll.cpu().numpy()[:args.cpu_sample]
+        got = ll_first[:args.cpu_sample]
         relerr = float(np.max(np.abs(got - np.asarray(vals_c)) / np.abs(np.asarray(vals_c))))
-        cpu = {'value': v_inv, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+        cpu = {'value': v_inv, 'unit': UNIT, 'cores': threads, 'host_cpus': os.cpu_count(), 'kind': 'port',
                'sample': '%d evals at N=%d of the same workload (rank 0 chains 0..%d): oracle port of sliceSample.py:136-147 '
-                         'as written (dense inv), numpy/scipy OpenBLAS on all host threads' % (args.cpu_sample, n, args.cpu_sample - 1),
+                         'as written (dense inv), numpy/scipy OpenBLAS, %d threads in effect' % (args.cpu_sample, n, args.cpu_sample - 1, threads),
                'restated_unit_value': v_chol, 'restated_unit': 'cdist+exp, dpotrf, one solve_triangular, log-diag',
                'gpu_vs_oracle_max_rel_err': relerr}
 
@@ -330,11 +573,9 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(n, B, world),
-                       l2='per-step working set %d matrices x %.0f MiB >> 126 MB L2 (no flush needed)' % (B, n * n * 8 / 2 ** 20),
-                       collective='one all_gather of loglik per step' if world > 1 else 'none (single rank)'),
+        'config': workload_config(n, B, world),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(sum(v[1] for v in prof.values())),
-        'roofline': roofline, 'cpu_baseline': cpu,
+        'roofline': roofline, 'cpu_baseline': cpu, 'configs': configs,
     }
     sys.stdout.flush()
     emit(line)
@@ -363,6 +604,7 @@ def emit(line):
 
 def main():
     args = parse()
+    set_blas_threads()                   # before numpy/scipy load their BLAS (both arms time a CPU sample)
     protect_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

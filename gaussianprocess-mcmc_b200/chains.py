@@ -28,7 +28,7 @@ class ChainEnsemble(object):
     ``(Hyp[B,P], loglik[B], ntrips[B])`` as numpy arrays on every rank."""
 
     def __init__(self, x, y, F0, Hyp0, scale, seed=0, max_trips=64, sweeper=None, gather_f=False, sharded_input=False,
-                 distributed=True):
+                 distributed=True, strict=False):
         self.x = np.asarray(x, dtype=np.float64)
         if self.x.ndim == 1:
             self.x = self.x.reshape(-1, 1)
@@ -36,6 +36,14 @@ class ChainEnsemble(object):
         self.my = float(np.mean(self.y))                       # sliceSample.py:102
         self.scale = np.asarray(scale, dtype=np.float64).reshape(-1)
         self.seed, self.max_trips, self.gather_f = int(seed), int(max_trips), gather_f
+        # A chain whose slice does not close within ``max_trips`` proposals keeps its state and is reported with
+        # status 1 (the reference's ``while True`` would loop on, or raise LinAlgError out of jitchol when the
+        # factorisation at the current state is the reason).  ``strict`` turns that into an exception; otherwise the
+        # ensemble counts such transitions (``exhausted_total``) and warns once per sweep.
+        self.strict = bool(strict)
+        self.exhausted_total = 0
+        self.last_status = None            # gathered status[B] of the last sweep (0 accepted, 1 trip budget used up)
+        self.last_busy_ms = None           # device time of this rank's local sweep (CUDA events), None for test doubles
         self.dist = None
         self.rank, self.world = 0, 1
         try:
@@ -78,30 +86,45 @@ class ChainEnsemble(object):
 
     def sweep(self, it):
         """One transition of every chain at MCMC iteration ``it``; returns gathered ``(Hyp, loglik, ntrips)``."""
-        hyp, ll, nt = self._sweeper.sweep(it)                  # local shard, [n_local, ...] tensors/arrays
-        return self._gather(hyp, ll, nt)
+        res = self._sweeper.sweep(it)                          # local shard, [n_local, ...] tensors/arrays
+        hyp, ll, nt = res[0], res[1], res[2]
+        status = res[3] if len(res) > 3 else None              # test doubles may not report a status
+        self.last_busy_ms = getattr(self._sweeper, 'last_busy_ms', None)
+        H, LL, NT, ST = self._gather(hyp, ll, nt, status)
+        self.last_status = ST
+        n_bad = int((ST != 0).sum())
+        if n_bad:
+            self.exhausted_total += n_bad
+            msg = ('%d of %d chains did not close their slice within max_trips=%d proposals at iteration %d (state kept; '
+                   'first: chain %d)' % (n_bad, self.n_chains, self.max_trips, it, int(np.flatnonzero(ST)[0])))
+            if self.strict:
+                raise RuntimeError(msg)
+            import warnings
+            warnings.warn(msg, RuntimeWarning)
+        return H, LL, NT
 
     def local_state(self):
         return self._sweeper.state()
 
-    def _gather(self, hyp, ll, nt):
+    def _gather(self, hyp, ll, nt, status=None):
         import torch
         P = self.P
-        pack = torch.cat([torch.as_tensor(hyp, dtype=torch.float64).reshape(self.n_local, P),
-                          torch.as_tensor(ll, dtype=torch.float64).reshape(self.n_local, 1),
-                          torch.as_tensor(nt).to(torch.float64).reshape(self.n_local, 1)], dim=1)
+        ll_t = torch.as_tensor(ll, dtype=torch.float64).reshape(self.n_local, 1)
+        st_t = torch.zeros_like(ll_t) if status is None else torch.as_tensor(status).to(ll_t.device, torch.float64).reshape(self.n_local, 1)
+        pack = torch.cat([torch.as_tensor(hyp, dtype=torch.float64).reshape(self.n_local, P), ll_t,
+                          torch.as_tensor(nt).to(torch.float64).reshape(self.n_local, 1), st_t], dim=1)
         if self.dist is None:
             out = pack
         else:
-            # ONE all-gather of [theta, loglik, ntrips] per sweep; shards may differ by one chain, so pad to the max
+            # ONE all-gather of [theta, loglik, ntrips, status] per sweep; shards may differ by one chain, so pad to the max
             mx = max(self._counts)
-            buf = torch.zeros((mx, P + 2), dtype=torch.float64, device=pack.device)
+            buf = torch.zeros((mx, P + 3), dtype=torch.float64, device=pack.device)
             buf[:self.n_local] = pack
-            full = torch.empty((self.world * mx, P + 2), dtype=torch.float64, device=pack.device)
+            full = torch.empty((self.world * mx, P + 3), dtype=torch.float64, device=pack.device)
             self.dist.all_gather_into_tensor(full, buf)
             out = torch.cat([full[r * mx: r * mx + c] for r, c in enumerate(self._counts)], dim=0)
         out = out.cpu().numpy()
-        return out[:, :P].copy(), out[:, P].copy(), out[:, P + 1].astype(np.int64)
+        return out[:, :P].copy(), out[:, P].copy(), out[:, P + 1].astype(np.int64), out[:, P + 2].astype(np.int64)
 
     def run(self, iters, start_iter=0, thin_f=0):
         """The caller loop of ``framework.py:68-75`` for the ensemble: returns ``histHyp[B, P, iters]``,
@@ -138,9 +161,15 @@ class _DeviceSweeper(object):
 
     def sweep(self, it):
         e = self.ens
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         nt, ll, status = ops.sds_sweep(self.x, self.y, self.F, self.H, self.scale, it, my=e.my, seed=e.seed,
                                        chain0=e.lo, max_trips=e.max_trips)
-        return self.H, ll, nt
+        e1.record()
+        e1.synchronize()
+        self.last_busy_ms = e0.elapsed_time(e1)
+        return self.H, ll, nt, status
 
     def state(self):
         return self.F.cpu().numpy(), self.H.cpu().numpy()

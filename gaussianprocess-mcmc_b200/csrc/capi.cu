@@ -126,7 +126,7 @@ size_t gpmc_workspace_bytes(int op, int N, int D, int B)
         // W per item + (for the jitter ladder) a backup of every matrix + ladder scratch
         // (sized for a caller ld <= N rounded up to 16)
         return (size_t)B * w + (size_t)B * (size_t)N * (size_t)ld_for(N) * sizeof(double)
-               + 3 * align_up((size_t)B * sizeof(double), 256) + 256;
+               + 4 * align_up((size_t)B * sizeof(double), 256) + 256;
     }
     if (op == GPMC_OP_LOGLIK) {
         const LoglikLayout l = loglik_layout(N, B);
@@ -158,7 +158,8 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     if (ld < N || (ld & 1)) { set_error("potrf: ld=%d must be even and >= N=%d (pad the matrix)", ld, N); return GPMC_EALIGN; }
     const size_t wbytes = (size_t)B * NB * NB * sizeof(double);
     const size_t mat_bytes = (size_t)B * N * ld * sizeof(double);
-    const size_t need = wbytes + (jitter_policy == GPMC_JITTER_PYGPS ? mat_bytes + 3 * align_up((size_t)B * sizeof(double), 256) + 256 : 0);
+    if (B > MAX_BATCH_ITEMS) { set_error("potrf: B=%d exceeds %d items per call (grid.y limit); split the batch", B, MAX_BATCH_ITEMS); return GPMC_EINVAL; }
+    const size_t need = wbytes + (jitter_policy == GPMC_JITTER_PYGPS ? mat_bytes + 4 * align_up((size_t)B * sizeof(double), 256) + 256 : 0);
     if (!ws_dev || ws_bytes < need) { set_error("potrf: workspace %zu < %zu bytes", ws_bytes, need); return GPMC_ENOMEM; }
     char *wp = (char *)ws_dev;
     double *W = (double *)wp; wp += wbytes;
@@ -171,7 +172,8 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     double *backup = (double *)wp; wp += mat_bytes;
     double *mean_dev = (double *)wp; wp += align_up((size_t)B * sizeof(double), 256);
     double *jit_dev = (double *)wp; wp += align_up((size_t)B * sizeof(double), 256);
-    int *map_dev = (int *)wp;
+    int *map_dev = (int *)wp; wp += align_up((size_t)B * sizeof(int), 256);
+    int *bad_dev = (int *)wp;
     GPMC_CUDA_CHECK(cudaMemcpyAsync(backup, A_dev, mat_bytes, cudaMemcpyDeviceToDevice, s));
     int rc = potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s);
     if (rc) return rc;
@@ -184,15 +186,12 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
 
     // diag statistics of the ORIGINAL matrices
     BatchView Bk{backup, (long long)N * ld, ld, nullptr, nullptr};
-    int *bad_dev = nullptr;
-    GPMC_CUDA_CHECK(cudaMalloc(&bad_dev, B * sizeof(int)));
     { int rc0 = diag_stats(Bk, N, mean_dev, bad_dev, B, s); if (rc0) return rc0; }
     std::vector<double> mean(B);
     std::vector<int> bad(B);
     GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), mean_dev, B * sizeof(double), cudaMemcpyDeviceToHost, s));
     GPMC_CUDA_CHECK(cudaMemcpyAsync(bad.data(), bad_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s));
     GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-    cudaFree(bad_dev);
     std::vector<double> jit(B, 0.0);
     std::vector<int> todo;
     for (int i : failed) {
@@ -205,6 +204,7 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
         GPMC_CUDA_CHECK(cudaMemcpyAsync(jit_dev, jit.data(), B * sizeof(double), cudaMemcpyHostToDevice, s));
         BatchView Am{A_dev, (long long)N * ld, ld, map_dev, nullptr};
         restore_jitter_kernel<<<dim3(64, nf), 256, 0, s>>>(Am, backup, N, jit_dev);
+        GPMC_LAUNCH_CHECK();
         for (int i : todo) info[i] = 0;
         GPMC_CUDA_CHECK(cudaMemcpyAsync(info_dev, info.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
         rc = potrf_sequence(Am, N, nf, info_dev, W, NB * NB, 0, zero_upper, s);
@@ -239,7 +239,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
     int *map_dev = (int *)wp; wp += align_up((size_t)B * sizeof(int), 256);
     wp += 256;
     wp += align_up((size_t)32 * l.ld * sizeof(double), 256);      // (reserved: vector scratch)
-    const size_t wave_cap = (ws_bytes - l.fixed_bytes) / l.per_item_bytes;
+    const size_t wave_cap = std::min<size_t>((ws_bytes - l.fixed_bytes) / l.per_item_bytes, (size_t)MAX_BATCH_ITEMS);   // items ride in grid.y
     const int wave = (int)std::min<size_t>(wave_cap, (size_t)B);
     double *mats = (double *)wp;
     double *W = (double *)(wp + (size_t)wave * l.mat_elems * sizeof(double));

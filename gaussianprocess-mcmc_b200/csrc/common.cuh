@@ -13,6 +13,7 @@ namespace gpmc {
 constexpr int NB = GPMC_NB;        // panel width of the blocked Cholesky (64 or 128)
 static_assert(NB == 64 || NB == 128, "panel width must be 64 or 128");
 constexpr int MAX_ELL = 8;         // max number of length-scales (ARD input dimension)
+constexpr int MAX_BATCH_ITEMS = 32768;   // batch items of one launch ride in grid.y / grid.z (limit 65535)
 
 // kernel classes for the profiling hooks (gpmc_profile_read)
 enum KernelClass { KC_ASSEMBLE = 0, KC_GEMM = 1, KC_POTF2 = 2, KC_TRSM = 3, KC_SOLVE = 4, KC_INV = 5, KC_SYRK_R = 6, KC_VEC = 7, KC_COUNT = 8 };
@@ -40,6 +41,22 @@ void prof_end(int kc, cudaStream_t s);
             return (int)_e;                                                                   \
         }                                                                                     \
     } while (0)
+
+// Per-device "do this once" latch: function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) belong to the
+// device that was current when they were set, so a process that drives several GPUs must set them once PER DEVICE.
+struct DeviceOnce {
+    unsigned long long mask[4] = {0, 0, 0, 0};
+    bool first()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return true;
+        unsigned long long &w = mask[(dev >> 6) & 3];
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (w & bit) return false;
+        w |= bit;
+        return true;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Batched matrix view.  Item b of a launch is matrix `map ? map[b] : b` of the allocation, so a

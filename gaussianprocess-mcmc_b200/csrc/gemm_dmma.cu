@@ -142,12 +142,9 @@ static int g_gemm_cfg = 4;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
 template <typename K>
-static int launch_variant(K kernel, const GemmArgs &a, int B, int bn, int threads, int smem, int kclass, cudaStream_t s, bool &attr_set)
+static int launch_variant(K kernel, const GemmArgs &a, int B, int bn, int threads, int smem, int kclass, cudaStream_t s, DeviceOnce &attr_set)
 {
-    if (!attr_set) {
-        GPMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    if (attr_set.first()) GPMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles_m = (a.rows + BM - 1) / BM;
     const int tiles_n = (a.cols + bn - 1) / bn;
     const int tiles = a.lower_only ? (BM / bn) * tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
@@ -167,7 +164,8 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
                   a.k0, a.bk0, a.cc0, a.A.ld, a.B.ld, a.C.ld);
         return GPMC_EALIGN;
     }
-    static bool set0 = false, set1 = false, set2 = false, env_read = false;
+    static DeviceOnce set0, set1, set2;
+    static bool env_read = false;
     if (!env_read) {            // GPMC_GEMM_CFG=0..3 selects the tile-kernel variant (experiments / A-B tests)
         const char *e = getenv("GPMC_GEMM_CFG");
         if (e && e[0] >= '0' && e[0] <= '4') g_gemm_cfg = e[0] - '0';

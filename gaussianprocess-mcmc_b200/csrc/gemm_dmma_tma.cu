@@ -286,11 +286,10 @@ int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cud
 {
     int rc = get_encoder();
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
-        attr_set = true;
     }
     CUtensorMap tmA, tmB;
     // rows at or beyond (origin + extent) are out of bounds for the TMA unit -> zero fill

@@ -268,10 +268,9 @@ int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *
                  int B, cudaStream_t s)
 {
     if (B <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
-        attr_set = true;
     }
     prof_begin(KC_POTF2, s);
     potf2_inv_kernel<<<B, POTF2_THREADS, POTF2_SMEM, s>>>(A, n, j0, W, strideW, info, zero_upper);

@@ -231,10 +231,9 @@ potf2_lite_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
 int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper, int B, cudaStream_t s)
 {
     if (B <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(potf2_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LITE_SMEM));
-        attr_set = true;
     }
     prof_begin(KC_POTF2, s);
     potf2_lite_kernel<<<B, LITE_THREADS, LITE_SMEM, s>>>(A, n, j0, W, strideW, info, zero_upper);

@@ -217,7 +217,8 @@ int launch_solve_reduce(BatchView L, int n, const double *a, const double *b, in
 {
     if (B <= 0) return 0;
     if (n > SOLVE_MAX_N) { set_error("solve_reduce: n=%d exceeds %d", n, SOLVE_MAX_N); return GPMC_EINVAL; }
-    GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    static DeviceOnce attr_set;
+    if (attr_set.first()) GPMC_CUDA_CHECK(cudaFuncSetAttribute(solve_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (B < 32 && n >= 1024 && zout && !b && (n % NB) == 0 && (ldv & 1) == 0) {
         // right-looking in launches; zout doubles as the working right-hand side
         copy_vec_mapped_kernel<<<dim3((n + 255) / 256, B), 256, 0, s>>>(L, n, a, zout, ldv);   // items may be mapped slots

@@ -347,7 +347,7 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
     if (tape_U && tape_trips < 1) { set_error("sds_sweep: tape_U given with tape_trips=%d", tape_trips); return GPMC_EINVAL; }
     if (B == 0) return 0;
     // chains per wave from the workspace
-    int cap = B;
+    int cap = std::min(B, MAX_BATCH_ITEMS);            // chains ride in grid.y
     while (cap > 1 && sweep_bytes(N, P, cap) > ws_bytes) cap = (cap + 1) / 2;
     if (!ws_dev || sweep_bytes(N, P, cap) > ws_bytes) {
         set_error("sds_sweep: workspace %zu bytes cannot hold one chain (%zu needed)", ws_bytes, sweep_bytes(N, P, 1));

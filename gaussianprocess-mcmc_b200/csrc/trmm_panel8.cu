@@ -87,10 +87,9 @@ int launch_trmm_panel8(BatchView A, int rows, int c0, int width, const double *W
 {
     if (B <= 0 || rows <= 0) return 0;
     if ((A.ld & 1) || (c0 & 1)) { set_error("trmm_panel: ld=%d c0=%d must be even", A.ld, c0); return GPMC_EALIGN; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(trmm_panel8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M8_SMEM));
-        attr_set = true;
     }
     // column pairs starting at or beyond the padded width do not exist in memory (the last block column of a ragged N);
     // the pad columns inside ld are zero and W_i is identity padded, so they are rewritten with zeros

@@ -192,10 +192,9 @@ int launch_trsm_panel(BatchView A, int n_rows, int j0, const double *W, long lon
     if (B <= 0 || rows <= 0) return 0;
     if (rows > 1 && rows % TP_ROWS == 1) rows -= 1;         // 128 k + 1: the extra row rides in the last CTA
     if ((A.ld & 1) || (j0 & 1)) { set_error("trsm_panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
-        attr_set = true;
     }
     dim3 grid((rows + TP_ROWS - 1) / TP_ROWS, B);
     prof_begin(KC_TRSM, s);

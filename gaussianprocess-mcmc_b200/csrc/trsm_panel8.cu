@@ -231,10 +231,9 @@ int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, 
 {
     if (B <= 0 || n <= 0) return 0;
     if (A.ld & 1) { set_error("inv_blocks: ld=%d must be even", A.ld); return GPMC_EALIGN; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(inv_blocks8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
-        attr_set = true;
     }
     const int nt = (n + NB - 1) / NB;
     dim3 grid(2 * nt, B);
@@ -251,10 +250,9 @@ int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long lo
     if (B <= 0 || rows <= 0) return 0;
     if ((A.ld & 1) || (j0 & 1)) { set_error("trsm_panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
     if (rows > 1 && rows % T8_ROWS == 1) rows -= 1;         // 64 k + 1: the extra row rides in the last CTA
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
-        attr_set = true;
     }
     dim3 grid((rows + T8_ROWS - 1) / T8_ROWS, B);
     prof_begin(KC_TRSM, s);

@@ -91,7 +91,7 @@ def potrf_batched(A, jitter_policy=JITTER_NONE, zero_upper=True, n=None, workspa
     info = torch.empty((B,), dtype=torch.int32, device='cuda')
     need = B * 128 * 128 * 8
     if jitter_policy == JITTER_PYGPS:
-        need += B * N * ld * 8 + 3 * ((B * 8 + 255) // 256 * 256) + 256
+        need += B * N * ld * 8 + 4 * ((B * 8 + 255) // 256 * 256) + 256
     ws = (workspace or _default_ws).get(torch, need)
     rc = lib.gpmc_potrf_batched(A.data_ptr(), N, ld, B, info.data_ptr(), jitter_policy, 1 if zero_upper else 0,
                                 ws.data_ptr(), ws.numel(), _stream_ptr(torch))
@@ -226,6 +226,7 @@ def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max
         ttrips = tape.U.shape[1]
     wsobj = workspace or _default_ws
     have = 0 if wsobj.buf is None else wsobj.buf.numel()
+    explicit_wave = chains_per_wave is not None
     if chains_per_wave is None:
         chains_per_wave = B
         if lib.gpmc_sds_workspace_bytes(N, P, B) > have:
@@ -233,14 +234,18 @@ def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max
             budget = (free + have) * 6 // 10
             while chains_per_wave > 1 and lib.gpmc_sds_workspace_bytes(N, P, chains_per_wave) > max(budget, have):
                 chains_per_wave = (chains_per_wave + 1) // 2
-    ws = wsobj.get(torch, lib.gpmc_sds_workspace_bytes(N, P, min(B, chains_per_wave)))
+    need = lib.gpmc_sds_workspace_bytes(N, P, min(B, chains_per_wave))
+    ws = wsobj.get(torch, need)
+    # the library sizes its waves from ws_bytes: an explicit chains_per_wave must really limit the wave even when the
+    # shared workspace is already larger
+    ws_bytes = need if explicit_wave else ws.numel()
     ptr = lambda t: None if t is None else t.data_ptr()
     rc = lib.gpmc_sds_sweep(x.data_ptr(), y.data_ptr(), N, D, F.data_ptr(), Hyp.data_ptr(), B, P, kind,
                             scale.data_ptr(), k.data_ptr(), th.data_ptr(), int(it),
                             my, 0.0 - my, 100.0 - my, int(seed), int(chain0),
                             ptr(tz), ptr(tv), ptr(tu), ptr(tU), ttrips, int(max_trips), jitter_policy,
                             ntrips.data_ptr(), loglik.data_ptr(), status.data_ptr(),
-                            ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+                            ws.data_ptr(), ws_bytes, _stream_ptr(torch))
     _lib.check(rc, 'gpmc_sds_sweep')
     return ntrips, loglik, status
 
