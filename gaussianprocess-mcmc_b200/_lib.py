@@ -45,6 +45,7 @@ SIGNATURES = {
     'gpmc_set_tuning': (_i, [_i, _i]),
     'gpmc_bench_fp64_peak': (_i, [_i, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'gpmc_bench_dmma_ilp': (_i, [_i, _i, _i, ctypes.POINTER(ctypes.c_double)]),
+    'gpmc_sds_loop_stats': (_i, [ctypes.POINTER(ctypes.c_longlong)] * 3),
     'gpmc_profile_enable': (_i, [_i]),
     'gpmc_profile_read': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     'gpmc_profile_reset': (_i, []),

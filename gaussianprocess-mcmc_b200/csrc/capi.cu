@@ -390,7 +390,16 @@ int gpmc_set_tuning(int key, int value)
     if (key == 2) { set_lookahead_mode(value); return 0; }
     if (key == 3) { set_potrf_window(value); return 0; }
     if (key == 4) { set_trsm_mode(value); return 0; }
+    if (key == 5) { set_trsm_blocks_per_cta(value); return 0; }
+    if (key == 6) { set_sds_mode(value); return 0; }
+    if (key == 7) { set_sds_runahead(value); return 0; }
     return GPMC_EINVAL;
+}
+
+int gpmc_sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders)
+{
+    sds_loop_stats(rounds, idle_rounds, ladders);
+    return 0;
 }
 
 int gpmc_profile_enable(int on) { g_prof_on = (on != 0); return 0; }

@@ -118,9 +118,13 @@ int launch_potf2(BatchView A, int n, int j0, double *W, long long strideW, int *
 // launch_trsm_panel8 reads); 2 CTAs per SM.  Not for callers that go on to inverse_sequence or use launch_trsm_panel.
 int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                       int B, cudaStream_t s);
+// potf2_reg.cu : same contract as launch_potf2_lite; the block lives in registers as DMMA fragments over 8 warps and is
+// factored in 16 steps of 8 columns (the default panel factor kernel)
+int launch_potf2_reg(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
+                     int B, cudaStream_t s);
 void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on
 void set_potrf_window(int w);      // override the window of the windowed schedule (multiple of NB; 0 = default)
-void set_potf2_mode(int mode);     // 0 / 2: the lite kernel whenever the full inverse is not needed (default), 1: always the full one
+void set_potf2_mode(int mode);     // 0: register-resident kernel (default), 2: the shared-memory lite kernel, 1: always the full-inverse one
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
@@ -133,6 +137,7 @@ int launch_trmm_panel8(BatchView A, int rows, int c0, int width, const double *W
 //   (W: nt blocks of NB x NB per item, item stride strideW)
 int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, cudaStream_t s);
 void set_trsm_mode(int mode);      // 0: trsm_panel8 (default), 1: trsm_panel (32-column sub-blocks)
+void set_trsm_blocks_per_cta(int v);   // 0: auto (1, 2 or 4 by launch size), else forced
 
 // solve_reduce.cu : z = L^-1 (a - b), optional outputs: z, loglik = -(0.5 z.z + sum log L_ii + 0.5 n log 2pi)
 //   a, b, zout are per-item vectors with row stride ldv (b, zout, loglik may be nullptr)
@@ -145,6 +150,11 @@ int launch_quad_logdet(BatchView L, int n, const double *z, int ldv, double *log
 //   mode 1: out = add - svec * (T x)   (m = g - S (K+S)^-1 g with T = L^-T, x = L^-1 g; sliceSample.py:204)
 int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const double *add, const double *svec,
                 int ldv, double *out, int B, cudaStream_t s);
+
+// sweep.cu
+void set_sds_mode(int mode);       // 0: resident loop (default), 1: wave loop
+void set_sds_runahead(int r);      // rounds queued ahead of the last status word seen (0: auto)
+void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);
 
 // microbench.cu
 int run_fp64_peak(int which, int iters, double *tflops, double *ms);

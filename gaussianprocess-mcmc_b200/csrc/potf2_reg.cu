@@ -1,0 +1,221 @@
+// Panel factor kernel, third form: the 128x128 diagonal block lives in REGISTERS as 8x8 DMMA accumulator fragments
+// spread over 8 warps, and is factored right-looking in 16 steps of 8 columns.  Used wherever potf2_lite.cu was
+// (kcGP.tools.jitchol call sites sliceSample.py:196,205): same inputs, same outputs (L11 in place, the sixteen 8x8
+// diagonal inverses in W, LAPACK-style info), about a quarter of its latency.
+//
+// Why: potf2_lite spends 42 % of its time in ONE warp that walks the 32 columns of a 32x32 sub-block with a row per
+// lane (ncu stall sampling, round 1) while the other warps wait, and stages the block through 90 KB of shared memory.
+// Here the sequential part shrinks to an 8x8 factorisation per step (one warp, row per lane, ~1000 cycles), and
+// everything else is DMMA work on register-resident fragments:
+//
+//   step b = 0..15  (block column b of 8x8 fragments)
+//     A  the warp that owns fragment (b,b) factors it:  L8 (and W8 = L8^-1) -> shared memory and global memory
+//     B  owners of fragments (r,b), r > b:  X = A W8^T, r = A - X L8^T, X += r W8^T  (inverse-multiply + one step of
+//        iterative refinement, the scheme of trsm_panel8.cu) -> global memory and the shared panel buffer
+//     C  every fragment (r,c), c > b:  acc -= X_r X_c^T   (2 DMMAs; X_r is the owner's own register pair -- with the
+//        contraction index of m8n8k4 permuted (k-step 0: k = 2 fk, k-step 1: k = 2 fk + 1) an accumulator pair IS the
+//        A-operand pair -- and X_c is one 16-byte shared-memory load)
+//   two block barriers per step; the owner of (b+1,b+1) updates that fragment first and starts factoring while the
+//   others finish their updates.
+//
+// Ownership: warp w holds block rows w and 15-w = 17 fragments = 34 doubles per lane, in slots with COMPILE-TIME
+// register indices (slot s <= w: fragment (w, s); slot s > w: fragment (15-w, s-w-1)); which fragment a slot holds is
+// a warp-uniform runtime value, so each step walks the 17 slots with warp-uniform predicates.  Shared memory: 10 KB;
+// registers bound the occupancy at two CTAs (two matrices) per SM, which hides one CTA's single-warp phase A behind
+// the other's DMMA phases.
+#include "common.cuh"
+#include "../../include/gpmc.h"
+
+namespace gpmc {
+
+static_assert(NB == 128 || NB == 64, "potf2_reg: panel width 64 or 128");
+constexpr int PR_NF = NB / 8;                 // 8x8 fragments per block row / column (16)
+constexpr int PR_WARPS = PR_NF / 2;           // 8 warps: warp w owns block rows w and PR_NF-1-w
+constexpr int PR_THREADS = PR_WARPS * 32;
+constexpr int PR_SLOTS = PR_NF + 1;           // (w + 1) + (PR_NF - w) fragments per warp
+
+__device__ __forceinline__ void dmma884_r(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// 1/sqrt(a) for the pivot chain: the hardware approximation (MUFU.RSQ64H, ~2^-22) plus two Newton steps,
+// y <- y + y (1/2 - (a/2) y^2): 6 dependent FP64 operations instead of the ~25 instructions (special-case handling
+// included) of the library rsqrt(), which sat on the critical path of every one of the 128 pivots.  Result within 1-2 ulp;
+// a <= 0 or NaN gives NaN / inf, which is what a failed pivot is allowed to produce (info is set by the caller).
+__device__ __forceinline__ double pivot_rsqrt(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-(h * y), y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-(h * y), y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
+__global__ void __launch_bounds__(PR_THREADS, 2)
+potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info, int zero_upper)
+{
+    __shared__ __align__(16) double sD[64];              // diagonal fragment on its way to the row-per-lane layout
+    __shared__ __align__(16) double sL8[64], sW8[64];    // factor of the current diagonal fragment and its inverse (zeros above)
+    __shared__ __align__(16) double sX[PR_NF][64];       // solved fragments X[block row][8][8] of the current block column
+    __shared__ int s_fail;
+    const int item = blockIdx.x;
+    if (A.count && item >= *A.count) return;
+    const int m = batch_item(A, item);
+    double *Ab = A.base + (size_t)m * A.stride + (size_t)j0 * A.ld + j0;
+    double *Wb = W + (size_t)m * strideW;
+    const int ld = A.ld;
+    const int nv = min(NB, n - j0);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rowA = w, rowB = PR_NF - 1 - w;
+
+    if (tid == 0) s_fail = 0;
+    // ---- the block's lower fragments straight into registers (rows / columns beyond the matrix: identity)
+    double acc[PR_SLOTS][2];
+#pragma unroll
+    for (int s = 0; s < PR_SLOTS; ++s) {
+        const int R = (s <= w) ? rowA : rowB;
+        const int C = (s <= w) ? s : s - w - 1;
+        const int gr = R * 8 + fr, gc = C * 8 + 2 * fk;
+        double2 v = make_double2(0.0, 0.0);
+        if (gr < nv && gc < nv) v = *reinterpret_cast<const double2 *>(Ab + (size_t)gr * ld + gc);
+        if (gr >= nv || gc >= nv) v.x = (gr == gc) ? 1.0 : 0.0;
+        if (gr >= nv || gc + 1 >= nv) v.y = (gr == gc + 1) ? 1.0 : 0.0;
+        acc[s][0] = v.x;
+        acc[s][1] = v.y;
+    }
+    double xa0 = 0.0, xa1 = 0.0, xb0 = 0.0, xb1 = 0.0;   // solved fragments of rows rowA / rowB in the current block column
+    __syncthreads();
+
+#pragma unroll 1
+    for (int b = 0; b < PR_NF; ++b) {
+        // ------------------------------------------------------------------ A: 8x8 diagonal fragment, one warp
+        const bool own_diag = (b < PR_WARPS) ? (w == b) : (w == PR_NF - 1 - b);
+        if (own_diag) {
+            const int dslot = (b < PR_WARPS) ? b : PR_SLOTS - 1;
+#pragma unroll
+            for (int s = 0; s < PR_SLOTS; ++s)
+                if (s == dslot) *reinterpret_cast<double2 *>(&sD[fr * 8 + 2 * fk]) = make_double2(acc[s][0], acc[s][1]);
+            __syncwarp();
+            // row (lane & 7) per lane; the four replicas compute the same thing, so every shuffle source is valid
+            const int r8 = lane & 7;
+            double a[8], x[8];
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(&sD[r8 * 8 + c]);
+                a[c] = (c <= r8) ? v.x : 0.0;
+                a[c + 1] = (c + 1 <= r8) ? v.y : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = (c == r8) ? 1.0 : 0.0;
+            int fail = 0;
+            double piv = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (!(piv > 0.0) && fail == 0) fail = j0 + b * 8 + c + 1;           // dpotf2: ajj <= 0 or NaN
+                const double rinv = pivot_rsqrt(piv);
+                a[c] = (r8 == c) ? piv * rinv : a[c] * rinv;
+                x[c] = x[c] * rinv;
+                if (c < 7) {
+                    // the next pivot first (it is the critical path of the whole kernel): row c+1 holds both a[c+1] and its
+                    // own multiplier l_{c+1,c}, so the value needs no shuffle before it is broadcast
+                    piv = __shfl_sync(0xffffffffu, fma(-a[c], a[c], a[c + 1]), c + 1);
+                }
+#pragma unroll
+                for (int j = c + 1; j < 8; ++j) {
+                    const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+                    a[j] = fma(-a[c], ljc, a[j]);
+                    x[j] = fma(-x[c], ljc, x[j]);                                   // lane k ends with column k of L8^-1
+                }
+            }
+            if (lane < 8) {
+                const int gr = b * 8 + r8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2 *>(&sL8[r8 * 8 + c]) = make_double2((c <= r8) ? a[c] : 0.0, (c + 1 <= r8) ? a[c + 1] : 0.0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    sW8[c * 8 + r8] = x[c];                                         // W8[c][k = r8]; zero for c < k
+                    Wb[(size_t)(b * 8 + c) * NB + b * 8 + r8] = x[c];
+                    if (c <= r8 && gr < nv) Ab[(size_t)gr * ld + b * 8 + c] = a[c];
+                }
+                if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;           // the FIRST failing pivot (later ones are NaN)
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------------ B: fragments (r, b), r > b
+        {
+            const double2 wv = *reinterpret_cast<const double2 *>(&sW8[fr * 8 + 2 * fk]);
+            const double2 lv = *reinterpret_cast<const double2 *>(&sL8[fr * 8 + 2 * fk]);
+#pragma unroll
+            for (int s = 0; s < PR_SLOTS; ++s) {
+                const bool isA = (s <= w);
+                const int R = isA ? rowA : rowB;
+                const int C = isA ? s : s - w - 1;
+                if (C == b && R > b) {
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma884_r(x0, x1, acc[s][0], wv.x);                             // X0 = A W8^T
+                    dmma884_r(x0, x1, acc[s][1], wv.y);
+                    double r0 = acc[s][0], r1 = acc[s][1];
+                    dmma884_r(r0, r1, -x0, lv.x);                                   // r = A - X0 L8^T
+                    dmma884_r(r0, r1, -x1, lv.y);
+                    dmma884_r(x0, x1, r0, wv.x);                                    // X = X0 + r W8^T
+                    dmma884_r(x0, x1, r1, wv.y);
+                    *reinterpret_cast<double2 *>(&sX[R][fr * 8 + 2 * fk]) = make_double2(x0, x1);
+                    if (isA) { xa0 = x0; xa1 = x1; } else { xb0 = x0; xb1 = x1; }
+                    const int gr = R * 8 + fr, gc = b * 8 + 2 * fk;
+                    if (gr < nv) {
+                        if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(x0, x1);
+                        else if (gc < nv) Ab[(size_t)gr * ld + gc] = x0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------------ C: fragments (r, c), c > b
+#pragma unroll
+        for (int s = 0; s < PR_SLOTS; ++s) {
+            const bool isA = (s <= w);
+            const int R = isA ? rowA : rowB;
+            const int C = isA ? s : s - w - 1;
+            if (C > b) {
+                const double n0 = isA ? -xa0 : -xb0, n1 = isA ? -xa1 : -xb1;
+                double2 xc;
+                if (C == R) xc = make_double2(-n0, -n1);                            // diagonal fragment: X_c is this warp's own pair
+                else xc = *reinterpret_cast<const double2 *>(&sX[C][fr * 8 + 2 * fk]);
+                dmma884_r(acc[s][0], acc[s][1], n0, xc.x);
+                dmma884_r(acc[s][0], acc[s][1], n1, xc.y);
+            }
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0 && s_fail != 0) {
+        if (info[m] == 0) info[m] = s_fail;
+    }
+    if (zero_upper) {
+        for (int e = tid; e < nv * nv; e += PR_THREADS) {
+            const int r = e / nv, c = e - r * nv;
+            if (c > r) Ab[(size_t)r * ld + c] = 0.0;
+        }
+    }
+}
+
+int launch_potf2_reg(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    if ((A.ld & 1) || (j0 & 1)) { set_error("potf2: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
+    prof_begin(KC_POTF2, s);
+    potf2_reg_kernel<<<B, PR_THREADS, 0, s>>>(A, n, j0, W, strideW, info, zero_upper);
+    prof_end(KC_POTF2, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace gpmc

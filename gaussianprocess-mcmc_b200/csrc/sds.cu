@@ -78,17 +78,29 @@ __device__ double density_sum(double head, const double *hyp, const double *pk, 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
 {
-    const int c = blockIdx.x;                          // every chain of the wave
+    // wave path: every chain of the wave (slot == chain of the wave); resident loop: the slots admitted this round
+    int c = blockIdx.x, gid = blockIdx.x;
+    if (st.chain_of) {
+        if (blockIdx.x >= *st.count_new) return;
+        c = st.map_new[blockIdx.x];
+        gid = st.chain_of[c];
+    }
     const int P = st.P, n = st.n;
-    const double *hyp = st.hyp + (size_t)c * P;
     __shared__ double s_S;
+    if (st.chain_of) {
+        // the chain's current state comes straight from the caller's arrays into the slot rows
+        for (int p = threadIdx.x; p < P; p += blockDim.x) st.hyp_stage[(size_t)c * P + p] = st.hyp_glob[(size_t)gid * P + p];
+        for (int i = threadIdx.x; i < st.ldv; i += blockDim.x) st.F_stage[(size_t)c * st.ldv + i] = (i < n) ? st.F_glob[(size_t)gid * n + i] : 0.0;
+        __syncthreads();
+    }
+    const double *hyp = st.hyp + (size_t)c * P;
     if (threadIdx.x == 0) {
         s_S = s_diag_value(hyp[P - 2], hyp[P - 1]);
         // bracket (:110-112): v ~ U(0, scale); hyp_min = max(hyp - v, 0); hyp_max = hyp_min + scale
         for (int p = 0; p < P; ++p) {
             double u;
-            if (st.tape_v) u = st.tape_v[(size_t)c * P + p];
-            else { double u1; philox_uniform2(st.seed, st.chain0 + c, st.sweep, STREAM_BRACKET, p, u, u1); }
+            if (st.tape_v) u = st.tape_v[(size_t)gid * P + p];
+            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_BRACKET, p, u, u1); }
             const double v = 0.0 + (st.scale[p] - 0.0) * u;
             const double lo = fmax(hyp[p] - v, 0.0);
             st.hyp_min[(size_t)c * P + p] = lo;
@@ -96,23 +108,26 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
             st.theta[(size_t)c * P + p] = hyp[p];      // the aux model is first evaluated at the current theta
         }
         double u0;
-        if (st.tape_u0) u0 = st.tape_u0[c];
-        else { double u1; philox_uniform2(st.seed, st.chain0 + c, st.sweep, STREAM_BRACKET, 1000, u0, u1); }
+        if (st.tape_u0) u0 = st.tape_u0[gid];
+        else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_BRACKET, 1000, u0, u1); }
         st.log_u0[c] = log(u0);
         st.done[c] = 0;
         st.ntrips[c] = 0;
-        st.map[c] = c;
-        if (c == 0) *st.count = gridDim.x;
+        if (st.chain_of) { st.parked[c] = 0; st.resolved[c] = 0; }
+        else {
+            st.map[c] = c;
+            if (c == 0) *st.count = gridDim.x;
+        }
     }
     __syncthreads();
     const double S = s_S, sd = sqrt(S);
     const double *f = st.F + (size_t)c * st.ldv;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double z;
-        if (st.tape_z) z = st.tape_z[(size_t)c * n + i];
+        if (st.tape_z) z = st.tape_z[(size_t)gid * n + i];
         else {
             double u0, u1;
-            philox_uniform2(st.seed, st.chain0 + c, st.sweep, STREAM_Z, i >> 1, u0, u1);
+            philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_Z, i >> 1, u0, u1);
             const double rad = sqrt(-2.0 * log(u0));
             z = (i & 1) ? rad * sin(6.283185307179586 * u1) : rad * cos(6.283185307179586 * u1);
         }
@@ -123,7 +138,14 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
 
 __global__ void __launch_bounds__(256) sds_threshold_kernel(SdsState st)
 {
-    const int c = blockIdx.x;
+    int c = blockIdx.x, gid = blockIdx.x;
+    if (st.chain_of) {
+        if (blockIdx.x >= *st.count_new) return;
+        c = st.map_new[blockIdx.x];
+        gid = st.chain_of[c];
+        // a factorisation of this evaluation failed and the jitter ladder (host side) has not run yet: wait for it
+        if ((st.info1[c] != 0 || st.info2[c] != 0) && !st.resolved[c]) { if (threadIdx.x == 0) st.parked[c] = 1; return; }
+    }
     __shared__ double red[8];
     const int P = st.P;
     const double *hyp = st.hyp + (size_t)c * P;
@@ -133,26 +155,40 @@ __global__ void __launch_bounds__(256) sds_threshold_kernel(SdsState st)
         st.cur_llk[c] = llk;
         st.threshold[c] = density_sum(st.log_u0[c] + llk, hyp, st.prior_k, st.prior_theta, P, st.G[c], st.iter);       // :127-129
         st.curG[c] = st.G[c];
+        if (st.chain_of) {
+            st.phase[c] = SDS_PHASE_ACTIVE;
+            if (st.loglik_glob) st.loglik_glob[gid] = st.G[c];     // what a chain that never accepts reports
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) sds_propose_kernel(SdsState st, int trip)
 {
-    if (blockIdx.x >= *st.count) return;
-    const int c = st.map[blockIdx.x];
+    int c, gid;
+    if (st.chain_of) {
+        if (blockIdx.x >= *st.count_act) return;
+        c = st.map_act[blockIdx.x];
+        gid = st.chain_of[c];
+        trip = st.ntrips[c];                           // chains of one round are at different trips
+    } else {
+        if (blockIdx.x >= *st.count) return;
+        c = st.map[blockIdx.x];
+        gid = c;
+    }
     const int P = st.P;
     __shared__ double s_S;
     if (threadIdx.x == 0) {
         double *th = st.theta + (size_t)c * P;
         for (int p = 0; p < P; ++p) {
             double u;
-            if (st.tape_U) u = st.tape_U[((size_t)c * st.tape_trips + trip) * P + p];
-            else { double u1; philox_uniform2(st.seed, st.chain0 + c, st.sweep, STREAM_TRIP, trip * 64 + p, u, u1); }
+            if (st.tape_U) u = st.tape_U[((size_t)gid * st.tape_trips + trip) * P + p];
+            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_TRIP, trip * 64 + p, u, u1); }
             const double lo = st.hyp_min[(size_t)c * P + p], hi = st.hyp_max[(size_t)c * P + p];
             th[p] = lo + (hi - lo) * u;                                                 // :132
         }
         if (st.iter < 500) th[P - 1] = st.hyp[(size_t)c * P + P - 1];                  // :133-134
         s_S = s_diag_value(th[P - 2], th[P - 1]);
+        if (st.chain_of) st.resolved[c] = 0;
     }
     __syncthreads();
     const double S = s_S;
@@ -161,8 +197,17 @@ __global__ void __launch_bounds__(256) sds_propose_kernel(SdsState st, int trip)
 
 __global__ void __launch_bounds__(256) sds_accept_kernel(SdsState st)
 {
-    if (blockIdx.x >= *st.count) return;
-    const int c = st.map[blockIdx.x];
+    int c, gid;
+    if (st.chain_of) {
+        if (blockIdx.x >= *st.count_act) return;
+        c = st.map_act[blockIdx.x];
+        gid = st.chain_of[c];
+        if ((st.info1[c] != 0 || st.info2[c] != 0) && !st.resolved[c]) { if (threadIdx.x == 0) st.parked[c] = 1; return; }
+    } else {
+        if (blockIdx.x >= *st.count) return;
+        c = st.map[blockIdx.x];
+        gid = c;
+    }
     __shared__ double red[8];
     __shared__ int s_accept;
     const int P = st.P;
@@ -177,21 +222,39 @@ __global__ void __launch_bounds__(256) sds_accept_kernel(SdsState st)
         st.last_llk[c] = llk;
         if (ok) {
             st.done[c] = 1;
-            for (int p = 0; p < P; ++p) st.hyp_out[(size_t)c * P + p] = th[p];
-            st.loglik_out[c] = st.G[c];
+            if (st.chain_of) {
+                for (int p = 0; p < P; ++p) st.hyp_glob_out[(size_t)gid * P + p] = th[p];
+                if (st.loglik_glob) st.loglik_glob[gid] = st.G[c];
+                if (st.ntrips_glob) st.ntrips_glob[gid] = st.ntrips[c];
+                if (st.status_glob) st.status_glob[gid] = 0;
+            } else {
+                for (int p = 0; p < P; ++p) st.hyp_out[(size_t)c * P + p] = th[p];
+                st.loglik_out[c] = st.G[c];
+            }
         } else {
             const double *h = st.hyp + (size_t)c * P;
             for (int p = 0; p < P; ++p) {                                                                           // :159-163
                 if (th[p] < h[p]) st.hyp_min[(size_t)c * P + p] = th[p];
                 else st.hyp_max[(size_t)c * P + p] = th[p];
             }
+            if (st.chain_of && st.ntrips[c] >= st.max_trips) {
+                // the trip budget ran out (the reference's `while True` would go on): the chain keeps its state
+                st.done[c] = 1;
+                if (st.ntrips_glob) st.ntrips_glob[gid] = st.ntrips[c];
+                if (st.status_glob) st.status_glob[gid] = 1;
+            }
         }
         s_accept = ok ? 1 : 0;
     }
     __syncthreads();
     if (s_accept) {
-        double *fo = st.F_out + (size_t)c * st.ldv;
-        for (int i = threadIdx.x; i < st.n; i += blockDim.x) fo[i] = fp[i];                                         // :156
+        if (st.chain_of) {
+            double *fo = st.F_glob_out + (size_t)gid * st.n;
+            for (int i = threadIdx.x; i < st.n; i += blockDim.x) fo[i] = fp[i];                                     // :156
+        } else {
+            double *fo = st.F_out + (size_t)c * st.ldv;
+            for (int i = threadIdx.x; i < st.n; i += blockDim.x) fo[i] = fp[i];                                     // :156
+        }
     }
 }
 
@@ -218,6 +281,80 @@ __global__ void __launch_bounds__(1024) sds_compact_kernel(SdsState st, int ncha
         __syncthreads();
     }
     if (threadIdx.x == 0) *st.count = s_count;
+}
+
+// Resident loop, once per round (one CTA): slots whose chain finished (or that never held one) take the next waiting
+// chains of the call, then the three slot lists of the round are rebuilt in slot order:
+//   map / count          every occupied slot that is not parked      (the auxiliary model is evaluated for these)
+//   map_new / count_new  slots admitted now                          (evaluate at the current theta: :104-129)
+//   map_act / count_act  slots inside their shrink loop              (propose, evaluate, accept / shrink: :131-163)
+// and the status word the host polls (without synchronising) is published.
+__device__ __forceinline__ int block_excl_rank(int flag, int *warp_cnt, int &total)
+{
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();                                   // warp_cnt is reused from the previous call
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { if (w < warp) off += warp_cnt[w]; tot += warp_cnt[w]; }
+    total = tot;
+    return off + __popc(bal & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(1024) sds_admit_kernel(SdsState st, int round)
+{
+    __shared__ int warp_cnt[32];
+    __shared__ int s_next, s_all, s_new, s_act, s_parked;
+    if (threadIdx.x == 0) { s_next = *st.next_chain; s_all = s_new = s_act = s_parked = 0; }
+    __syncthreads();
+    for (int base = 0; base < st.cap; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int is_free = (c < st.cap) && (st.chain_of[c] < 0 || st.done[c] != 0);
+        int total;
+        const int rank = block_excl_rank(is_free, warp_cnt, total);
+        const int next = s_next;
+        if (is_free) {
+            const int id = next + rank;
+            if (id < st.n_chains) { st.chain_of[c] = id; st.phase[c] = SDS_PHASE_NEW; st.parked[c] = 0; st.resolved[c] = 0; st.ntrips[c] = 0; }
+            else { st.chain_of[c] = -1; st.phase[c] = SDS_PHASE_FREE; }
+            st.done[c] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = min(st.n_chains, next + total);
+        __syncthreads();
+    }
+    for (int base = 0; base < st.cap; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const bool occ = (c < st.cap) && st.chain_of[c] >= 0;
+        const bool pk = occ && st.parked[c] != 0;
+        const int ph = occ ? st.phase[c] : SDS_PHASE_FREE;
+        const int f_all = occ && !pk, f_new = f_all && ph == SDS_PHASE_NEW, f_act = f_all && ph == SDS_PHASE_ACTIVE;
+        int t_all, t_new, t_act, t_pk;
+        const int r_all = block_excl_rank(f_all, warp_cnt, t_all);
+        const int r_new = block_excl_rank(f_new, warp_cnt, t_new);
+        const int r_act = block_excl_rank(f_act, warp_cnt, t_act);
+        (void)block_excl_rank(pk ? 1 : 0, warp_cnt, t_pk);
+        if (f_all) st.map[s_all + r_all] = c;
+        if (f_new) st.map_new[s_new + r_new] = c;
+        if (f_act) st.map_act[s_act + r_act] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) { s_all += t_all; s_new += t_new; s_act += t_act; s_parked += t_pk; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *st.next_chain = s_next;
+        *st.count = s_all; *st.count_new = s_new; *st.count_act = s_act;
+        st.status_word[SDS_SW_COUNT] = s_all; st.status_word[SDS_SW_NEW] = s_new; st.status_word[SDS_SW_ACT] = s_act;
+        st.status_word[SDS_SW_PARKED] = s_parked; st.status_word[SDS_SW_NEXT] = s_next; st.status_word[SDS_SW_ROUND] = round;
+    }
+}
+
+int launch_sds_admit(const SdsState &st, int round, cudaStream_t s)
+{
+    sds_admit_kernel<<<1, 1024, 0, s>>>(st, round);
+    GPMC_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_sds_begin(const SdsState &st, int nchains, cudaStream_t s)

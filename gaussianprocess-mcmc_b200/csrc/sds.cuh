@@ -28,6 +28,26 @@ struct SdsState {
     double *log_u0, *threshold, *cur_llk, *curG, *last_proposal, *last_llk;   // [B]
     int *done, *ntrips;            // [B]
     int *map, *count;              // active list
+    // ---- resident loop only (gpmc_sds_sweep, default path; all nullptr / 0 on the wave path).  Rows of the work
+    // arrays above are SLOTS; a slot holds chain chain_of[slot] of the call (or -1), chains are admitted into free
+    // slots on the device, and inputs / results move between the caller's arrays and the slot rows inside the kernels.
+    int *chain_of;                 // [cap] chain of the call held by the slot, -1 = free
+    int *phase;                    // [cap] SDS_PHASE_*
+    int *parked, *resolved;        // [cap] factorisation failed: wait for the host-side jitter ladder / ladder done
+    const int *info1, *info2;      // [cap] status of chol(K+S) and chol(R + 1e-11 I) of the evaluation just queued
+    int *map_new, *count_new;      // slots admitted this round (evaluate at the current theta)
+    int *map_act, *count_act;      // slots in their shrink loop (evaluate at a proposal)
+    int *status_word;              // [8]: count, count_new, count_act, parked, next_chain, round
+    int *next_chain;               // next chain of the call to admit
+    int n_chains, cap, max_trips;
+    const double *F_glob;          // [n_chains, n] caller's latent vectors (in; overwritten on accept)
+    double *F_glob_out;
+    const double *hyp_glob;        // [n_chains, P]
+    double *hyp_glob_out;
+    int *ntrips_glob, *status_glob;   // [n_chains] (may be nullptr)
+    double *loglik_glob;           // [n_chains] (may be nullptr)
+    double *hyp_stage;             // [cap, P] slot copy of the chain's current theta (== hyp on this path)
+    double *F_stage;               // [cap, ldv] slot copy of the chain's current f (== F on this path)
     // explicit randomness (all nullptr -> Philox)
     const double *tape_z;          // [B, n]
     const double *tape_v;          // [B, P]
@@ -36,10 +56,15 @@ struct SdsState {
     int tape_trips;
 };
 
+enum { SDS_PHASE_FREE = 0, SDS_PHASE_NEW = 1, SDS_PHASE_ACTIVE = 2 };
+enum { SDS_SW_COUNT = 0, SDS_SW_NEW = 1, SDS_SW_ACT = 2, SDS_SW_PARKED = 3, SDS_SW_NEXT = 4, SDS_SW_ROUND = 5, SDS_SW_WORDS = 8 };
+
 int launch_sds_begin(const SdsState &st, int nchains, cudaStream_t s);
 int launch_sds_threshold(const SdsState &st, int nchains, cudaStream_t s);
 int launch_sds_propose(const SdsState &st, int nactive, int trip, cudaStream_t s);
 int launch_sds_accept(const SdsState &st, int nactive, cudaStream_t s);
 int launch_sds_compact(const SdsState &st, int nchains, cudaStream_t s);
+// resident loop: admit waiting chains into free slots, rebuild the three slot lists, publish the status word
+int launch_sds_admit(const SdsState &st, int round, cudaStream_t s);
 
 }  // namespace gpmc

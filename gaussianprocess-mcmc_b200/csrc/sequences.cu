@@ -289,8 +289,9 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 GPMC_CUDA_CHECK(cudaEventRecord(la->ev_q, sQ));
                 GPMC_CUDA_CHECK(cudaStreamWaitEvent(sP, la->ev_q, 0));
             }
-            rc = lite ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
-                      : launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP);
+            rc = !lite ? launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
+                 : (g_potf2_mode == 2 ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
+                                      : launch_potf2_reg(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP));
             if (rc) return rc;
             if (j0 + NB < n && (rc = (g_trsm_mode == 1 ? launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP)
                                                         : launch_trsm_panel8(A, nr, j0, Wj, strideW, B, sP)))) return rc;

@@ -34,6 +34,8 @@ struct SweepBuffers {
     double *theta, *hyp_min, *hyp_max, *hyp_in, *hyp_out;         // [cap, P]
     double *G, *log_u0, *threshold, *cur_llk, *curG, *last_prop, *last_llk, *jit, *mean, *loglik_out;   // [cap]
     int *done, *ntrips, *map, *count, *info1, *info2, *bad, *fmap;   // ints
+    int *chain_of, *phase, *parked, *resolved, *map_new, *map_act;   // resident loop (sds.cuh)
+    int *count_new, *count_act, *status_word, *next_chain;           // (inside the 256-byte block of `count`)
 };
 
 static char *carve(char *&p, size_t bytes) { char *r = p; p += align_up(bytes, 256); return r; }
@@ -56,9 +58,11 @@ static size_t layout(SweepBuffers &w, char *base, int n, int P, int cap)
     for (double **v : hyps) *v = (double *)carve(p, (size_t)P * 8 * cap);
     double **scal[] = {&w.G, &w.log_u0, &w.threshold, &w.cur_llk, &w.curG, &w.last_prop, &w.last_llk, &w.jit, &w.mean, &w.loglik_out};
     for (double **v : scal) *v = (double *)carve(p, (size_t)8 * cap);
-    int **ints[] = {&w.done, &w.ntrips, &w.map, &w.info1, &w.info2, &w.bad, &w.fmap};
+    int **ints[] = {&w.done, &w.ntrips, &w.map, &w.info1, &w.info2, &w.bad, &w.fmap,
+                    &w.chain_of, &w.phase, &w.parked, &w.resolved, &w.map_new, &w.map_act};
     for (int **v : ints) *v = (int *)carve(p, (size_t)4 * cap);
-    w.count = (int *)carve(p, 256);
+    w.count = (int *)carve(p, 256);                  // [0] count, [16] ladder scratch count, then the resident loop's words
+    w.count_new = w.count + 24; w.count_act = w.count + 25; w.next_chain = w.count + 26; w.status_word = w.count + 32;
     return (size_t)(p - base);
 }
 
@@ -143,12 +147,13 @@ static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitem
 // The factorisations are run optimistically: chol(K+S), everything that follows from it, and chol(R + 1e-11 I) are
 // queued without looking at info[], then BOTH status vectors are read in one host synchronisation; only when a
 // factorisation failed (rare) does the pyGPs jitter ladder run, for the failed chains alone.
-static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
+// The optimistic pass: chol(K+S), everything that follows from it and chol(R + 1e-11 I) for the slots listed in
+// w.map / w.count (at most `na` of them), queued without looking at info[] -- no host synchronisation.
+static int aux_queue(const AuxCtx &c, int na)
 {
     SweepBuffers &w = *c.w;
     cudaStream_t s = c.s;
-    const int na = (int)active.size();
-    if (na == 0) return 0;
+    if (na <= 0) return 0;
     const long long mat = w.mat;
     BatchView A1{w.buf1, mat, w.ld, w.map, w.count};
     BatchView A2{w.buf2, mat, w.ld, w.map, w.count};
@@ -160,7 +165,19 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A1, na, s))) return rc;
     if ((rc = border_set(A1, w.n, w.g, w.ldv, na, s))) return rc;
     if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
-    if ((rc = aux_downstream(c, A1, A2, na))) return rc;
+    return aux_downstream(c, A1, A2, na);
+}
+
+static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
+{
+    SweepBuffers &w = *c.w;
+    cudaStream_t s = c.s;
+    const int na = (int)active.size();
+    if (na == 0) return 0;
+    const long long mat = w.mat;
+    const long long strideW = (long long)w.nt * NB * NB;
+    int rc;
+    if ((rc = aux_queue(c, na))) return rc;
     if (c.jitter_policy != GPMC_JITTER_PYGPS) return 0;
 
     // ---- one synchronisation: status of both factorisations
@@ -257,6 +274,196 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             todo.swap(still);
         }
         if ((rc = mark_not_pd(c, w.info2, todo))) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The resident loop (default).  The wave loop further down drains every wave to its slowest chain and reads a status
+// vector from the device after every trip; here the workspace is a set of SLOTS instead:
+//   * a round = [admit] -> begin (new slots) / propose (slots in their shrink loop) -> auxiliary model for every occupied
+//     slot -> whitening + threshold (new slots) / f' + accept-or-shrink (the others);
+//   * the admit kernel hands the slots of chains that accepted (or ran out of trips) to the next waiting chains of the
+//     call, so the number of matrices per launch stays at capacity until the call runs out of chains;
+//   * the host never waits for a round: it enqueues rounds ahead and polls, without blocking, a small status word that
+//     every round copies into pinned memory (how many slots are occupied, how many chains are still waiting); launches
+//     are sized by the last value seen (an upper bound -- the kernels cut at the device-side counts), and rounds that
+//     were queued after the last chain finished find empty lists and exit;
+//   * a factorisation that fails parks its slot (no decision is taken for it); when the host sees parked slots in the
+//     status word it drains the stream and runs the pyGPs jitter ladder for those slots alone (aux_eval), then resumes.
+// Results are those of the wave loop bit for bit: randomness and tapes are keyed by the chain, not by the slot or round.
+struct ResidentHost {
+    static constexpr int RING = 8;
+    int *pinned = nullptr;                      // RING status words
+    cudaEvent_t ev[RING] = {};
+    bool ok = false;
+};
+static ResidentHost *resident_host()
+{
+    static ResidentHost per_dev[64];
+    static bool tried[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    ResidentHost &h = per_dev[dev];
+    if (!tried[dev]) {
+        tried[dev] = true;
+        bool ok = cudaHostAlloc((void **)&h.pinned, ResidentHost::RING * SDS_SW_WORDS * sizeof(int), cudaHostAllocPortable) == cudaSuccess;
+        for (int i = 0; ok && i < ResidentHost::RING; ++i) ok = cudaEventCreateWithFlags(&h.ev[i], cudaEventDisableTiming) == cudaSuccess;
+        h.ok = ok;
+    }
+    return h.ok ? &h : nullptr;
+}
+
+static int g_sds_mode = 0;            // 0: resident loop, 1: wave loop
+static int g_sds_runahead = 0;        // rounds the host may queue ahead of the last status it has seen (0: auto)
+void set_sds_mode(int mode) { g_sds_mode = mode; }
+void set_sds_runahead(int r) { g_sds_runahead = r; }
+static long long g_sds_rounds = 0, g_sds_idle_rounds = 0, g_sds_ladders = 0;   // diagnostics of the last call
+void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders)
+{
+    if (rounds) *rounds = g_sds_rounds;
+    if (idle_rounds) *idle_rounds = g_sds_idle_rounds;
+    if (ladders) *ladders = g_sds_ladders;
+}
+
+static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, double *hyp_dev, int B, int P,
+                              int n_ell, const double *scale_dev, const double *prior_k_dev, const double *prior_theta_dev, int iter,
+                              double my, double lower, double upper, unsigned long long seed, unsigned chain0,
+                              const double *tape_z, const double *tape_v, const double *tape_u0, const double *tape_U, int tape_trips,
+                              int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
+                              SweepBuffers &w, cudaStream_t s)
+{
+    ResidentHost *rh = resident_host();
+    if (!rh) { set_error("sds_sweep: cannot allocate the pinned status ring"); return GPMC_ENOMEM; }
+    const int cap = w.cap;
+    AuxCtx ctx{x_dev, N, D, P, n_ell, &w, s, jitter_policy};
+    int rc;
+    // every slot free, nothing admitted yet
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.chain_of, 0xFF, (size_t)cap * 4, s));
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.done, 0, (size_t)cap * 4, s));
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.parked, 0, (size_t)cap * 4, s));
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.resolved, 0, (size_t)cap * 4, s));
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.phase, 0, (size_t)cap * 4, s));
+    GPMC_CUDA_CHECK(cudaMemsetAsync(w.count, 0, 256, s));
+    if (status_dev) GPMC_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, (size_t)B * 4, s));
+
+    SdsState st{};
+    st.n = N; st.P = P; st.ldv = w.ldv; st.iter = iter; st.sweep = (unsigned)iter; st.chain0 = chain0; st.seed = seed;
+    st.my = my; st.lower = lower; st.upper = upper;
+    st.y = y_dev; st.scale = scale_dev; st.prior_k = prior_k_dev; st.prior_theta = prior_theta_dev;
+    st.F = w.Fin; st.hyp = w.hyp_in; st.F_out = w.Fout; st.hyp_out = w.hyp_out; st.loglik_out = w.loglik_out;
+    st.g = w.g; st.svec = w.svec; st.fprop = w.fprop; st.theta = w.theta; st.hyp_min = w.hyp_min; st.hyp_max = w.hyp_max;
+    st.G = w.G; st.log_u0 = w.log_u0; st.threshold = w.threshold; st.cur_llk = w.cur_llk; st.curG = w.curG;
+    st.last_proposal = w.last_prop; st.last_llk = w.last_llk;
+    st.done = w.done; st.ntrips = w.ntrips; st.map = w.map; st.count = w.count;
+    st.tape_z = tape_z; st.tape_v = tape_v; st.tape_u0 = tape_u0; st.tape_U = tape_U; st.tape_trips = tape_trips;
+    st.chain_of = w.chain_of; st.phase = w.phase; st.parked = w.parked; st.resolved = w.resolved;
+    st.info1 = w.info1; st.info2 = w.info2;
+    st.map_new = w.map_new; st.count_new = w.count_new; st.map_act = w.map_act; st.count_act = w.count_act;
+    st.status_word = w.status_word; st.next_chain = w.next_chain;
+    st.n_chains = B; st.cap = cap; st.max_trips = tape_U ? std::min(max_trips, tape_trips) : max_trips;
+    st.F_glob = F_dev; st.F_glob_out = F_dev; st.hyp_glob = hyp_dev; st.hyp_glob_out = hyp_dev;
+    st.ntrips_glob = ntrips_dev; st.status_glob = status_dev; st.loglik_glob = loglik_dev;
+    st.hyp_stage = w.hyp_in; st.F_stage = w.Fin;
+
+    const BatchView C2all{w.buf2, w.mat, w.ld, w.map, w.count};
+    const BatchView C2new{w.buf2, w.mat, w.ld, w.map_new, w.count_new};
+    const BatchView C2act{w.buf2, w.mat, w.ld, w.map_act, w.count_act};
+    (void)C2all;
+
+    // what the host knows (stale, but on the safe side): chains admitted so far (only grows), occupied slots
+    int known_next = 0, known_count = cap, known_parked = 0;
+    bool finished = false;
+    long long round = 0, polled = 0;            // rounds queued / status words consumed
+    // run-ahead: deep enough that the device never waits for the host, shallow enough that the idle rounds queued past the
+    // end cost little next to a round of real work
+    const double round_flops = (double)std::min(cap, B) * (4.0 / 3.0) * (double)N * N * N;
+    int runahead = g_sds_runahead > 0 ? g_sds_runahead : (round_flops > 2e11 ? 4 : (round_flops > 2e9 ? 3 : 2));
+    runahead = std::min(runahead, ResidentHost::RING - 1);
+    g_sds_rounds = g_sds_idle_rounds = g_sds_ladders = 0;
+
+    auto consume = [&](bool block) -> int {
+        // read status words of completed rounds, oldest first
+        while (polled < round) {
+            const int slot = (int)(polled % ResidentHost::RING);
+            cudaError_t q = block ? cudaEventSynchronize(rh->ev[slot]) : cudaEventQuery(rh->ev[slot]);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+            if (q != cudaSuccess) { set_error("sds_sweep: status poll failed: %s", cudaGetErrorString(q)); return (int)q; }
+            const int *sw = rh->pinned + slot * SDS_SW_WORDS;
+            known_next = sw[SDS_SW_NEXT]; known_count = sw[SDS_SW_COUNT]; known_parked = sw[SDS_SW_PARKED];
+            if (known_count == 0 && known_parked == 0 && known_next >= B) finished = true;
+            if (known_count == 0) ++g_sds_idle_rounds;
+            ++polled;
+            block = false;                       // at most one blocking wait per call
+        }
+        return 0;
+    };
+
+    while (true) {
+        if ((rc = consume(round - polled >= runahead))) return rc;
+        if (finished) break;
+        if (known_parked > 0) {
+            // ---- rare path: a factorisation failed.  Let everything queued finish, then run the auxiliary model WITH the
+            // jitter ladder for the parked slots alone and take their pending decision.
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+            if ((rc = consume(false))) return rc;
+            std::vector<int> parked(cap), phase(cap);
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(parked.data(), w.parked, (size_t)cap * 4, cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(phase.data(), w.phase, (size_t)cap * 4, cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+            std::vector<int> ids, ids_new, ids_act, ones;
+            for (int c = 0; c < cap; ++c) if (parked[c]) { ids.push_back(c); (phase[c] == SDS_PHASE_NEW ? ids_new : ids_act).push_back(c); }
+            if (!ids.empty()) {
+                ++g_sds_ladders;
+                const int np = (int)ids.size(), nn = (int)ids_new.size(), nact = (int)ids_act.size();
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.map, ids.data(), (size_t)np * 4, cudaMemcpyHostToDevice, s));
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.count, &np, 4, cudaMemcpyHostToDevice, s));
+                if ((rc = aux_eval(ctx, ids))) return rc;                     // optimistic pass + ladder, synchronous
+                // decisions may be taken now whatever info[] says (a factorisation the ladder could not rescue is a
+                // non-finite, i.e. rejected, proposal -- :154)
+                std::vector<int> flags(cap, 0);
+                for (int c : ids) flags[c] = 1;
+                GPMC_CUDA_CHECK(cudaMemcpyAsync(w.resolved, flags.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, s));
+                GPMC_CUDA_CHECK(cudaMemsetAsync(w.parked, 0, (size_t)cap * 4, s));
+                if (nn) {
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(w.map_new, ids_new.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, s));
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(w.count_new, &nn, 4, cudaMemcpyHostToDevice, s));
+                    if ((rc = launch_solve_reduce(C2new, N, w.Fin, w.m, w.ldv, w.eta, nullptr, w.info2, nn, s))) return rc;
+                    if ((rc = launch_sds_threshold(st, nn, s))) return rc;
+                }
+                if (nact) {
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(w.map_act, ids_act.data(), (size_t)nact * 4, cudaMemcpyHostToDevice, s));
+                    GPMC_CUDA_CHECK(cudaMemcpyAsync(w.count_act, &nact, 4, cudaMemcpyHostToDevice, s));
+                    if ((rc = launch_trmv(C2act, N, 0, 0, w.eta, w.m, nullptr, w.ldv, w.fprop, nact, s))) return rc;
+                    if ((rc = launch_sds_accept(st, nact, s))) return rc;
+                }
+                GPMC_CUDA_CHECK(cudaStreamSynchronize(s));                    // the host vectors above die here
+            }
+            known_parked = 0;
+            known_count = cap;                   // the parked slots are back in the lists
+        }
+        // ---- one round, sized by what the host knows
+        const int nb_new = std::min(cap, B - known_next);                    // chains that can still be admitted
+        const int nb_all = known_next < B ? std::min(cap, B) : std::min(cap, known_count);
+        const int nb_act = nb_all;
+        if ((rc = launch_sds_admit(st, (int)round, s))) return rc;
+        {
+            const int slot = (int)(round % ResidentHost::RING);
+            GPMC_CUDA_CHECK(cudaMemcpyAsync(rh->pinned + slot * SDS_SW_WORDS, w.status_word, SDS_SW_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
+            GPMC_CUDA_CHECK(cudaEventRecord(rh->ev[slot], s));
+        }
+        ++round;
+        ++g_sds_rounds;
+        if (nb_all <= 0) { if ((rc = consume(true))) return rc; continue; }   // nothing can be running: wait for the word
+        if (nb_new > 0 && (rc = launch_sds_begin(st, nb_new, s))) return rc;                                       // :102-112,194
+        if ((rc = launch_sds_propose(st, nb_act, 0, s))) return rc;                                                 // :132-134
+        if ((rc = aux_queue(ctx, nb_all))) return rc;                                                               // :136-139,147
+        if (nb_new > 0) {
+            if ((rc = launch_solve_reduce(C2new, N, w.Fin, w.m, w.ldv, w.eta, nullptr, w.info2, nb_new, s))) return rc;   // eta, :108
+            if ((rc = launch_sds_threshold(st, nb_new, s))) return rc;                                              // :114-129
+        }
+        if ((rc = launch_trmv(C2act, N, 0, 0, w.eta, w.m, nullptr, w.ldv, w.fprop, nb_act, s))) return rc;          // f' = C eta + m, :140
+        if ((rc = launch_sds_accept(st, nb_act, s))) return rc;                                                     // :142-163
     }
     return 0;
 }
@@ -361,6 +568,11 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
         GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
         GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
     }
+    if (g_sds_mode == 0)
+        return sds_sweep_resident(x_dev, y_dev, N, D, F_dev, hyp_dev, B, P, n_ell, scale_dev, prior_k_dev, prior_theta_dev, iter,
+                                  my, lower, upper, seed, chain0, tape_z, tape_v, tape_u0, tape_U, tape_trips, max_trips,
+                                  jitter_policy, ntrips_dev, loglik_dev, status_dev, w, s);
+    // ---- wave loop (gpmc_set_tuning(6, 1)): kept for A/B and as the reference the resident loop is tested against
     AuxCtx ctx{x_dev, N, D, P, n_ell, &w, s, jitter_policy};
     std::vector<int> active;
     for (int c0 = 0; c0 < B; c0 += cap) {

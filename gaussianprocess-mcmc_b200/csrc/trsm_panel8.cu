@@ -44,7 +44,7 @@ __device__ __forceinline__ void dmma884_8(double &c0, double &c1, double a, doub
 }
 
 __global__ void __launch_bounds__(T8_THREADS, 2)
-trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW)
+trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW, int nblk)
 {
     extern __shared__ __align__(16) double sm[];
     double *Lb = sm;                              // 10 lower 32x32 blocks of L11
@@ -54,9 +54,6 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
     const int m = batch_item(A, b);
     double *Ab = A.base + (size_t)m * A.stride;
     const int ld = A.ld;
-    const int row0 = j0 + NB + blockIdx.x * T8_ROWS;
-    // n_rows counts a border row too; the last CTA takes every row that is left (at most 64 + 1)
-    const int rows_valid = (blockIdx.x == gridDim.x - 1) ? min(T8_ROWS + 8, n_rows - row0) : T8_ROWS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
 
@@ -76,15 +73,22 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wb + (size_t)(blk * 8 + r) * NB + blk * 8 + c2));
     }
     asm volatile("cp.async.commit_group;\n" ::);
+    // Row blocks of 64 rows are dealt round-robin to the CTAs of this matrix (blockIdx.x, stride gridDim.x): with many
+    // matrices in flight a CTA solves several row blocks against the L11 it staged once (the 108 KB prologue is what
+    // kept the DMMA pipe at 75 % when every CTA took a single block).
+    // n_rows counts a border row too; the last row block takes every row that is left (at most 64 + 1)
+    const int rb_first = blockIdx.x;
+    const int row0_first = j0 + NB + rb_first * T8_ROWS;
+    const int rv_first = (rb_first == nblk - 1) ? min(T8_ROWS + 8, n_rows - row0_first) : T8_ROWS;
     // this warp's 8 rows as accumulator fragments: acc[b8] = row warp*8 + fr, cols b8*8 + 2fk, +1
     double acc[T8_NB8][2];
     const int r_loc = warp * 8 + fr;
-    double *grow = Ab + (size_t)(row0 + min(r_loc, max(rows_valid, 1) - 1)) * ld + j0 + 2 * fk;
     {
+        const double *grow0 = Ab + (size_t)(row0_first + min(r_loc, max(rv_first, 1) - 1)) * ld + j0 + 2 * fk;
 #pragma unroll
         for (int b8 = 0; b8 < T8_NB8; ++b8) {
             double2 v = make_double2(0.0, 0.0);
-            if (r_loc < rows_valid) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
+            if (r_loc < rv_first) v = *reinterpret_cast<const double2 *>(grow0 + b8 * 8);
             acc[b8][0] = v.x;
             acc[b8][1] = v.y;
         }
@@ -101,8 +105,21 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
         if (c > r) W8[(blk * 8 + r) * T8_WS + c] = 0.0;
     }
     __syncthreads();
-    if (warp * 8 >= rows_valid) return;           // nothing to solve (no border row, or a ragged last CTA)
 
+    for (int rb = rb_first; rb < nblk; rb += gridDim.x) {
+    const int row0 = j0 + NB + rb * T8_ROWS;
+    const int rows_valid = (rb == nblk - 1) ? min(T8_ROWS + 8, n_rows - row0) : T8_ROWS;
+    if (warp * 8 >= rows_valid) continue;         // nothing to solve (no border row, or a ragged last block)
+    double *grow = Ab + (size_t)(row0 + min(r_loc, max(rows_valid, 1) - 1)) * ld + j0 + 2 * fk;
+    if (rb != rb_first) {
+#pragma unroll
+        for (int b8 = 0; b8 < T8_NB8; ++b8) {
+            double2 v = make_double2(0.0, 0.0);
+            if (r_loc < rows_valid) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
+            acc[b8][0] = v.x;
+            acc[b8][1] = v.y;
+        }
+    }
 #pragma unroll
     for (int b8 = 0; b8 < T8_NB8; ++b8) {
         const int sb = b8 >> 2, q = b8 & 3;
@@ -131,6 +148,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
         }
         // ---- the finished 8 columns leave from the accumulator registers (4 lanes x 16 bytes per row)
         if (r_loc < rows_valid) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
+    }
     }
 }
 
@@ -244,6 +262,9 @@ int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, 
     return 0;
 }
 
+static int g_trsm_blocks_per_cta = 0;
+void set_trsm_blocks_per_cta(int v) { g_trsm_blocks_per_cta = v; }
+
 int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s)
 {
     int rows = n_rows - j0 - NB;
@@ -254,9 +275,17 @@ int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long lo
     if (attr_set.first()) {
         GPMC_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
     }
-    dim3 grid((rows + T8_ROWS - 1) / T8_ROWS, B);
+    const int nblk = (rows + T8_ROWS - 1) / T8_ROWS;
+    // CTAs per matrix: one per row block while the launch would not fill the chip several times over, else up to
+    // four row blocks per CTA (g_trsm_blocks_per_cta overrides: experiments)
+    int per_cta = g_trsm_blocks_per_cta;
+    if (per_cta <= 0) {
+        const long long ctas = (long long)nblk * B;
+        per_cta = ctas >= 16 * 296 ? 4 : (ctas >= 8 * 296 ? 2 : 1);
+    }
+    dim3 grid((nblk + per_cta - 1) / per_cta, B);
     prof_begin(KC_TRSM, s);
-    trsm_panel8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n_rows, j0, W, strideW);
+    trsm_panel8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n_rows, j0, W, strideW, nblk);
     prof_end(KC_TRSM, s);
     GPMC_LAUNCH_CHECK();
     return 0;

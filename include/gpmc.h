@@ -180,12 +180,16 @@ int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ld
 
 /* Kernel tuning knobs for experiments.
  * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default).
- * key 1: panel factor kernel (0 = the diagonal-inverse kernel whenever the block inverse is not needed, 1 = always the
- *        full-inverse kernel).
+ * key 1: panel factor kernel (0 = the register-resident kernel potf2_reg.cu (default), 2 = the shared-memory kernel
+ *        potf2_lite.cu -- both emit the 8x8 diagonal inverses only --, 1 = always the full-inverse kernel potf2.cu).
  * key 2: look-ahead in the blocked Cholesky (panel kernels overlapped with the update GEMM on side streams):
  *        0 auto (on when at most #SMs/2 matrices are in flight), 1 off, 2 on.
  * key 3: window (columns, multiple of 128) of the windowed schedule used for few large matrices; 0 = default.
- * key 4: panel solve kernel: 0 = 8-column sub-blocks, 2 CTAs/SM (default), 1 = 32-column sub-blocks. */
+ * key 4: panel solve kernel: 0 = 8-column sub-blocks, 2 CTAs/SM (default), 1 = 32-column sub-blocks.
+ * key 5: 64-row blocks one CTA of the panel solve takes: 0 = auto (1, 2 or 4 by launch size), else forced.
+ * key 6: gpmc_sds_sweep loop: 0 = resident loop (slots refilled on the device, host polls a status word without
+ *        synchronising; default), 1 = wave loop (one status read per trip, waves drained to their slowest chain).
+ * key 7: rounds the resident loop queues ahead of the last status word it has seen (0 = auto: 2..4 by problem size). */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
@@ -199,6 +203,9 @@ int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_ou
  * (0 assemble, 1 Cholesky update GEMM, 2 panel potf2, 3 panel trsm, 4 solve+reduce, 5 triangular inverse,
  *  6 posterior-covariance SYRK, 7 vector/control kernels)
  * when enabled; used by bench.py for roofline.achieved. */
+/* Diagnostics of the last gpmc_sds_sweep on this thread: rounds queued, rounds that found nothing to do (queued past the
+ * end), times the host-side jitter ladder had to run. */
+int gpmc_sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);
 int gpmc_profile_enable(int on);
 int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches);
 int gpmc_profile_reset(void);

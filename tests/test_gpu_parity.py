@@ -130,8 +130,9 @@ def test_potrf_reports_lapack_info(gp):
 
 @pytest.mark.parametrize('n', [37, 128, 300, 1000])
 def test_both_panel_factor_kernels_agree(gp, so, n):
-    """potf2.cu (full block inverse, 1 CTA/SM) and potf2_lite.cu (diagonal sub-block inverses, 2 CTAs/SM) are picked by
-    batch size; force each in turn over the same matrices, incl. a non-PD one (LAPACK info must match)."""
+    """potf2_reg.cu (register-resident fragments, default = mode 0), potf2.cu (full block inverse, mode 1) and
+    potf2_lite.cu (shared-memory block, diagonal sub-block inverses, mode 2): force each in turn over the same matrices,
+    incl. a non-PD one (LAPACK info must match)."""
     import torch
     import scipy.linalg
     x = np.arange(n, dtype=np.float64).reshape(n, 1)
@@ -140,7 +141,7 @@ def test_both_panel_factor_kernels_agree(gp, so, n):
     bad = min(n - 1, 170)
     out = {}
     try:
-        for mode in (1, 2):
+        for mode in (0, 1, 2):
             gp.ops.set_tuning(1, mode)
             A = A0.clone()
             A[3, bad, bad] = -1.0
@@ -148,16 +149,18 @@ def test_both_panel_factor_kernels_agree(gp, so, n):
             out[mode] = (A.cpu().numpy()[:, :, :n], info)
     finally:
         gp.ops.set_tuning(1, 0)
-    (L1, i1), (L2, i2) = out[1], out[2]
-    assert np.array_equal(i1, i2) and np.all(i1[:3] == 0) and i1[3] == bad + 1
+    (L1, i1) = out[1]
     Ah = A0.cpu().numpy()[:, :, :n]
-    for b in range(3):
-        assert np.all(np.triu(L2[b], 1) == 0)
-        resid = np.linalg.norm(L2[b] @ L2[b].T - Ah[b]) / np.linalg.norm(Ah[b])
-        assert resid < 5e-15
-        ref = scipy.linalg.cholesky(Ah[b], lower=True)
-        np.testing.assert_allclose(np.diag(L2[b]), np.diag(ref), rtol=1e-12)
-        np.testing.assert_allclose(L2[b], L1[b], rtol=0, atol=1e-12 * np.abs(ref).max())
+    for mode in (0, 2):
+        L2, i2 = out[mode]
+        assert np.array_equal(i1, i2) and np.all(i1[:3] == 0) and i1[3] == bad + 1
+        for b in range(3):
+            assert np.all(np.triu(L2[b], 1) == 0)
+            resid = np.linalg.norm(L2[b] @ L2[b].T - Ah[b]) / np.linalg.norm(Ah[b])
+            assert resid < 5e-15, (mode, b, resid)
+            ref = scipy.linalg.cholesky(Ah[b], lower=True)
+            np.testing.assert_allclose(np.diag(L2[b]), np.diag(ref), rtol=1e-12)
+            np.testing.assert_allclose(L2[b], L1[b], rtol=0, atol=1e-12 * np.abs(ref).max())
 
 
 @pytest.mark.parametrize('n', [129, 193, 257, 300, 1000, 1153])

@@ -369,3 +369,41 @@ def test_sweep_survives_numerically_singular_states(gp, capfd):
     # the healthy chains are not disturbed by their singular neighbours
     F1, H1, n1, s1 = run([1])
     assert np.array_equal(H1[0], H[1]) and n1[0] == nt[1]
+
+
+def test_resident_loop_equals_wave_loop(gp):
+    """gpmc_sds_sweep's default loop keeps the chains in device-side slots that are refilled as chains finish and is
+    polled by the host without synchronising; the wave loop (gpmc_set_tuning(6, 1)) drains waves and reads a status vector
+    per trip.  Same chains, same tapes / Philox keys => the same results bit for bit, whatever the slot count."""
+    import torch
+    from gpmc_b200 import ops, _lib
+    import ctypes
+    n, B = 160, 23
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+
+    def run(mode, wave, it):
+        ops.set_tuning(6, mode)
+        try:
+            F = torch.tensor(F0.copy()).cuda(); H = torch.tensor(H0.copy()).cuda()
+            out = []
+            for k in range(2):
+                nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it + k, seed=31, max_trips=40, chains_per_wave=wave,
+                                           workspace=ops.Workspace())
+                out.append((nt.cpu().numpy(), ll.cpu().numpy(), st.cpu().numpy()))
+            return F.cpu().numpy(), H.cpu().numpy(), out
+        finally:
+            ops.set_tuning(6, 0)
+    for it in (0, 600):
+        ref = run(1, None, it)
+        for wave in (None, 5, 1):
+            got = run(0, wave, it)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+            for a, b in zip(got[2], ref[2]):
+                for u, v in zip(a, b):
+                    assert np.array_equal(u, v)
+    r, i, l = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+    _lib.load().gpmc_sds_loop_stats(ctypes.byref(r), ctypes.byref(i), ctypes.byref(l))
+    print('resident loop, last call: %d rounds queued, %d found nothing to do, %d ladder passes' % (r.value, i.value, l.value))
+    assert r.value >= 2
