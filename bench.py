@@ -291,7 +291,7 @@ def sub_loglik(gp, torch, np, name, n, B, ard, reps, peak_tf, n_check, what):
     return rec
 
 
-def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check, what, dist=None, world=1, rank=0):
+def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check, what, dist=None, world=1, rank=0, run_mode=False):
     """Device-resident SDS sweeps (whole surrogate_slice_sampling transitions for B chains PER RANK through
     ChainEnsemble): chain-sweeps/s, trips, 4/3 N^3 flop per auxiliary-model evaluation against the DGEMM rate,
     per-rank busy time (trip-count imbalance) and a tape-driven comparison with the oracle on sampled chains."""
@@ -316,10 +316,16 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     busy, trips = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(sweeps):
-        Hg, llg, ntg = ens.sweep(start_iter + 1 + i)        # gathered over ranks
+    if run_mode:
+        # the whole caller loop in ONE device call (gpmc_sds_run): chains advance on their own, one all-gather at the end
+        _, _, ntg = ens.run(sweeps, start_iter=start_iter + 1)
         busy.append(ens.last_busy_ms)
-        trips.append(ntg)
+        trips = [ntg[:, i] for i in range(sweeps)]
+    else:
+        for i in range(sweeps):
+            Hg, llg, ntg = ens.sweep(start_iter + 1 + i)    # gathered over ranks
+            busy.append(ens.last_busy_ms)
+            trips.append(ntg)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -340,7 +346,7 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     evals = int((trips + 1).sum())                          # aux-model evaluations: one at theta + one per trip
     flops = evals * (4.0 / 3.0) * n ** 3
     tf = flops / (ms * 1e-3) / 1e12
-    rec = {'name': name, 'kind': 'sds_sweep', 'workload': what, 'n': n, 'chains_per_gpu': B, 'chains': world * B,
+    rec = {'name': name, 'kind': 'sds_run' if run_mode else 'sds_sweep', 'workload': what, 'n': n, 'chains_per_gpu': B, 'chains': world * B,
            'ard_dims': ard, 'sweeps': sweeps, 'start_iter': start_iter + 1,
            's_per_sweep': ms * 1e-3 / sweeps, 'chain_sweeps_per_s': world * B * sweeps / (ms * 1e-3),
            'mean_trips': float(trips.mean()), 'max_trips': int(trips.max()), 'aux_evals': evals,
@@ -508,6 +514,11 @@ def run_b200(args):
                                        'BASELINE config 5 shard of the real sampler: N=%d, 256 chains per GPU, whole SDS '
                                        'transitions, chains sharded by GPU, one all-gather per sweep' % n,
                                        dist=dist, world=world, rank=rank))
+            if on('C5_sds_run'):
+                configs.append(sub_sds(gp, torch, np, 'C5_sds_run', n, 256, 0, 3, 0, peak_tf, 0,
+                                       'same shard, 3 MCMC iterations per chain in ONE device call (gpmc_sds_run: the caller loop '
+                                       'framework.py:68-75 on the device, no chain waits at an iteration boundary), one all-gather '
+                                       'of the history at the end', dist=dist, world=world, rank=rank, run_mode=True))
         except Exception as e:                              # a sub-record must never cost the headline line
             configs.append({'name': 'error', 'error': repr(e)})
 

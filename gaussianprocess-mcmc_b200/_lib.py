@@ -37,11 +37,19 @@ SIGNATURES = {
     'gpmc_sds_sweep': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i,
                             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_ulonglong, ctypes.c_uint,
                             _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gpmc_sds_run': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i,
+                          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_ulonglong, ctypes.c_uint, _i, _i,
+                          _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     'gpmc_aux_workspace_bytes': (_sz, [_i]),
     'gpmc_aux_var_model': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gpmc_trsv_lower_batched': (_i, [_vp, _i, _i, ctypes.c_longlong, _vp, _i, _i, _vp, _vp, _vp]),
     'gpmc_cov_cross': (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     'gpmc_tg2_loglik': (_i, [_vp, ctypes.c_double, _vp, _i, _i, _i, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp]),
+    'gpmc_predict_workspace_bytes': (_sz, [_i, _i, _i]),
+    'gpmc_predict_batched': (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gpmc_ess_workspace_bytes': (_sz, [_i, _i]),
+    'gpmc_ess_sweep': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                            ctypes.c_ulonglong, ctypes.c_uint, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gpmc_set_tuning': (_i, [_i, _i]),
     'gpmc_bench_fp64_peak': (_i, [_i, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'gpmc_bench_dmma_ilp': (_i, [_i, _i, _i, ctypes.POINTER(ctypes.c_double)]),

@@ -126,14 +126,41 @@ class ChainEnsemble(object):
         out = out.cpu().numpy()
         return out[:, :P].copy(), out[:, P].copy(), out[:, P + 1].astype(np.int64), out[:, P + 2].astype(np.int64)
 
-    def run(self, iters, start_iter=0, thin_f=0):
+    def run(self, iters, start_iter=0, thin_f=0, gather_every=None):
         """The caller loop of ``framework.py:68-75`` for the ensemble: returns ``histHyp[B, P, iters]``,
-        ``histLL[B, iters]``, ``trips[B, iters]`` (and the local ``histF[n_local, N, kept]`` when ``thin_f > 0``)."""
+        ``histLL[B, iters]``, ``trips[B, iters]`` (and the local ``histF[n_local, N, kept]`` when ``thin_f > 0``).
+
+        With the device sweeper the loop itself runs on the GPU (``gpmc_sds_run``): every chain of the shard goes through
+        its iterations back to back, and the ranks exchange their history in ONE all-gather per ``gather_every`` iterations
+        (default: once, at the end).  A sweeper without ``run`` (the CPU test double) is driven one sweep at a time."""
         B, P = self.n_chains, self.P
         histHyp = np.zeros((B, P, iters))
         histLL = np.zeros((B, iters))
         trips = np.zeros((B, iters), dtype=np.int64)
         keepF = []
+        if hasattr(self._sweeper, 'run') and iters > 0:
+            step = iters if not gather_every else max(1, int(gather_every))
+            for i0 in range(0, iters, step):
+                k = min(step, iters - i0)
+                # thinning is relative to the start of the run: keep f after iterations 0, thin_f, 2 thin_f, ...
+                hh, ll, nt, hf, n_exh = self._sweeper.run(start_iter + i0, k, thin_f, (-i0) % thin_f if thin_f else 0)
+                self.last_busy_ms = getattr(self._sweeper, 'last_busy_ms', None)
+                G = self._gather_block(hh, ll, nt)                         # [B, k, P + 2]
+                histHyp[:, :, i0:i0 + k] = np.transpose(G[:, :, :P], (0, 2, 1))
+                histLL[:, i0:i0 + k] = G[:, :, P]
+                trips[:, i0:i0 + k] = G[:, :, P + 1].astype(np.int64)
+                if hf is not None:
+                    keepF.append(hf)
+                if n_exh:
+                    self.exhausted_total += n_exh
+                    msg = '%d transitions of this rank\'s chains did not close their slice within max_trips=%d proposals (state kept)' % (n_exh, self.max_trips)
+                    if self.strict:
+                        raise RuntimeError(msg)
+                    import warnings
+                    warnings.warn(msg, RuntimeWarning)
+            if thin_f:
+                return histHyp, histLL, trips, np.concatenate(keepF, axis=-1)
+            return histHyp, histLL, trips
         for i in range(iters):
             h, ll, nt = self.sweep(start_iter + i)
             histHyp[:, :, i], histLL[:, i], trips[:, i] = h, ll, nt
@@ -142,6 +169,22 @@ class ChainEnsemble(object):
         if thin_f:
             return histHyp, histLL, trips, np.stack(keepF, axis=-1)
         return histHyp, histLL, trips
+
+    def _gather_block(self, hh, ll, nt):
+        """All-gather of a block of history ``[n_local, k, P + 2]`` -> ``[B, k, P + 2]`` (numpy) on every rank."""
+        import torch
+        P = self.P
+        k = hh.shape[1]
+        pack = torch.cat([hh, ll.reshape(self.n_local, k, 1), nt.to(torch.float64).reshape(self.n_local, k, 1)], dim=2).contiguous()
+        if self.dist is None:
+            return pack.cpu().numpy()
+        mx = max(self._counts)
+        buf = torch.zeros((mx, k, P + 2), dtype=torch.float64, device=pack.device)
+        buf[:self.n_local] = pack
+        full = torch.empty((self.world * mx, k, P + 2), dtype=torch.float64, device=pack.device)
+        self.dist.all_gather_into_tensor(full, buf)
+        out = torch.cat([full[r * mx: r * mx + c] for r, c in enumerate(self._counts)], dim=0)
+        return out.cpu().numpy()
 
 
 class _DeviceSweeper(object):
@@ -170,6 +213,25 @@ class _DeviceSweeper(object):
         e1.synchronize()
         self.last_busy_ms = e0.elapsed_time(e1)
         return self.H, ll, nt, status
+
+    def run(self, it0, n_iters, thin_f=0, thin_phase=0):
+        """``n_iters`` transitions of every local chain on the device; returns device history tensors and the local
+        ``histF[n_local, N, kept]`` (numpy) when ``thin_f > 0`` (f after the iterations ``thin_phase, thin_phase + thin_f, ...``
+        of this block)."""
+        e = self.ens
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if thin_f and thin_phase:
+            # blocks that do not start on a kept iteration: run up to the next kept one first
+            raise ValueError('gather_every must be a multiple of thin_f')
+        hh, ll, nt, hf, n_exh = ops.sds_run(self.x, self.y, self.F, self.H, self.scale, it0, n_iters, my=e.my, seed=e.seed,
+                                            chain0=e.lo, max_trips=e.max_trips, keep_f_every=thin_f)
+        e1.record()
+        e1.synchronize()
+        self.last_busy_ms = e0.elapsed_time(e1)
+        histF = None if hf is None else np.transpose(hf.cpu().numpy(), (0, 2, 1))
+        return hh, ll, nt, histF, n_exh
 
     def state(self):
         return self.F.cpu().numpy(), self.H.cpu().numpy()

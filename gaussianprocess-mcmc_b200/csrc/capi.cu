@@ -94,6 +94,56 @@ static LoglikLayout loglik_layout(int N, int B)
     return l;
 }
 
+// Assemble-and-factor one wave with kcGP.tools.jitchol semantics (pyGPs 1.3.4): one plain attempt for every item, then --
+// for the items that failed only -- any(diag <= 0) -> GPMC_INFO_NOT_PD, else the ladder mean(diag) * 1e-6 * 10^k, k < 5,
+// re-assembling the item with the jitter on its diagonal.  `fill` assembles the listed items INCLUDING their border
+// rows; `diag_value` is the (constant) diagonal of an item's matrix from its hyper-parameter row.
+int factor_wave(const std::function<int(BatchView, int, const double *)> &fill, const std::function<double(const double *)> &diag_value,
+                BatchView A, int N, int nb, const double *hyp_w, int P, int *info_w, double *W, double *jit_dev, int *map_dev,
+                int jitter_policy, int border_rows, cudaStream_t s)
+{
+    int rc = fill(A, nb, nullptr);
+    if (rc) return rc;
+    if ((rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s, border_rows))) return rc;
+    if (jitter_policy != GPMC_JITTER_PYGPS) return 0;
+    std::vector<int> info(nb);
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<int> todo;
+    for (int i = 0; i < nb; ++i) if (info[i] != 0) todo.push_back(i);
+    if (todo.empty()) return 0;
+    std::vector<double> hyp_host((size_t)nb * P);
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(hyp_host.data(), hyp_w, (size_t)nb * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<double> jit(nb, 0.0);
+    std::vector<int> keep;
+    for (int i : todo) {
+        const double dv = diag_value(&hyp_host[(size_t)i * P]);
+        if (dv <= 0.0) info[i] = GPMC_INFO_NOT_PD;       // any(diag <= 0): LinAlgError
+        else { jit[i] = dv * 1e-6; keep.push_back(i); }   // NaN diag also lands here and keeps failing
+    }
+    todo.swap(keep);
+    for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
+        const int nf = (int)todo.size();
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(map_dev, todo.data(), nf * sizeof(int), cudaMemcpyHostToDevice, s));
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(jit_dev, jit.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s));
+        for (int i : todo) info[i] = 0;
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(info_w, info.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        BatchView Am{A.base, A.stride, A.ld, map_dev, nullptr};
+        if ((rc = fill(Am, nf, jit_dev))) return rc;
+        if ((rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s, border_rows))) return rc;
+        GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<int> still;
+        for (int i : todo) if (info[i] != 0) { still.push_back(i); jit[i] *= 10.0; }
+        todo.swap(still);
+    }
+    for (int i : todo) info[i] = GPMC_INFO_NOT_PD;
+    GPMC_CUDA_CHECK(cudaMemcpyAsync(info_w, info.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
+    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // namespace gpmc
 
 using namespace gpmc;
@@ -245,59 +295,20 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
     double *W = (double *)(wp + (size_t)wave * l.mat_elems * sizeof(double));
 
     { int rc0 = fill_int(info_dev, 0, B, s); if (rc0) return rc0; }
-    std::vector<double> hyp_host;
     for (int s0 = 0; s0 < B; s0 += wave) {
         const int nb = std::min(wave, B - s0);
         const double *hyp_w = hyp_dev + (size_t)s0 * P;
         const double *g_w = g_dev + (size_t)s0 * N;
         int *info_w = info_dev + s0;
         BatchView A{mats, (long long)l.mat_elems, l.ld, nullptr, nullptr};
-        int rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A, nb, s);
+        auto fill = [&](BatchView V, int nitems, const double *jit) -> int {
+            int rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, jit, V, nitems, s);
+            if (rc) return rc;
+            return border_set(V, N, g_w, N, nitems, s);
+        };
+        auto diag = [&](const double *h) { return host_diag_value(h, n_ell); };
+        int rc = factor_wave(fill, diag, A, N, nb, hyp_w, P, info_w, W, jit_dev, map_dev, jitter_policy, 1, s);
         if (rc) return rc;
-        if ((rc = border_set(A, N, g_w, N, nb, s))) return rc;
-        rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s, 1);
-        if (rc) return rc;
-        if (jitter_policy == GPMC_JITTER_PYGPS) {
-            std::vector<int> info(nb);
-            GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-            GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-            std::vector<int> todo;
-            for (int i = 0; i < nb; ++i) if (info[i] != 0) todo.push_back(i);
-            if (!todo.empty()) {
-                hyp_host.resize((size_t)nb * P);
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(hyp_host.data(), hyp_w, (size_t)nb * P * sizeof(double), cudaMemcpyDeviceToHost, s));
-                GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-                std::vector<double> jit(nb, 0.0);
-                std::vector<int> keep;
-                for (int i : todo) {
-                    const double dv = host_diag_value(&hyp_host[(size_t)i * P], n_ell);
-                    if (dv <= 0.0) info[i] = GPMC_INFO_NOT_PD;       // any(diag <= 0): LinAlgError
-                    else { jit[i] = dv * 1e-6; keep.push_back(i); }   // NaN diag also lands here and keeps failing
-                }
-                todo.swap(keep);
-                for (int attempt = 0; attempt < 5 && !todo.empty(); ++attempt) {
-                    const int nf = (int)todo.size();
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(map_dev, todo.data(), nf * sizeof(int), cudaMemcpyHostToDevice, s));
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(jit_dev, jit.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s));
-                    for (int i : todo) info[i] = 0;
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(info_w, info.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
-                    BatchView Am{mats, (long long)l.mat_elems, l.ld, map_dev, nullptr};
-                    rc = launch_cov_assemble(x_dev, N, D, hyp_w, P, n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, jit_dev, Am, nf, s);
-                    if (rc) return rc;
-                    if ((rc = border_set(Am, N, g_w, N, nf, s))) return rc;
-                    rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s, 1);
-                    if (rc) return rc;
-                    GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
-                    GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-                    std::vector<int> still;
-                    for (int i : todo) if (info[i] != 0) { still.push_back(i); jit[i] *= 10.0; }
-                    todo.swap(still);
-                }
-                for (int i : todo) info[i] = GPMC_INFO_NOT_PD;
-                GPMC_CUDA_CHECK(cudaMemcpyAsync(info_w, info.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
-                GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
-            }
-        }
         // z = L^-1 g sits in the border row except for the last column block: finish it, then quad form + log det
         rc = border_finish(A, N, loglik_dev + s0, info_w, nb, s);
         if (rc) return rc;

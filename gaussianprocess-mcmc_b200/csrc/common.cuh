@@ -129,7 +129,10 @@ void set_potf2_mode(int mode);     // 0: register-resident kernel (default), 2: 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
 // trsm_panel8.cu : the same solve with 8-column sub-blocks, shuffle-based fragment conversion, 2 CTAs per SM (default)
-int launch_trsm_panel8(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);
+//   row_start >= 0: solve only rows row_start .. n-1 (border rows of the last block column); n_mat >= 0: order of the matrix
+//   (rows / columns of the diagonal block at or beyond it read as identity)
+int launch_trsm_panel8(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s,
+                       int row_start = -1, int n_mat = -1);
 // trmm_panel8.cu : in place  A[0:rows, c0:c0+width] = -(A[0:rows, c0:c0+128] W^T)  for a lower triangular 128x128 W
 //   (the second product of the triangular inverse, inverse_sequence)
 int launch_trmm_panel8(BatchView A, int rows, int c0, int width, const double *W, long long strideW, int B, cudaStream_t s);
@@ -148,6 +151,7 @@ int launch_quad_logdet(BatchView L, int n, const double *z, int ldv, double *log
 // trmv.cu : out = T x (+ add) for a triangular row-major T;  upper=0: lower triangle, upper=1: upper triangle.
 //   mode 0: out = T x + add            (f' = C eta + m, sliceSample.py:140)
 //   mode 1: out = add - svec * (T x)   (m = g - S (K+S)^-1 g with T = L^-T, x = L^-1 g; sliceSample.py:204)
+//   mode 2: out = T x                  (nu = chol(K) z, the draw of elliptical_slice; sliceSample.py:41)
 int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const double *add, const double *svec,
                 int ldv, double *out, int B, cudaStream_t s);
 

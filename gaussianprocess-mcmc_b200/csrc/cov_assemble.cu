@@ -46,7 +46,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
     __shared__ double s_ui[MAX_ELL][AT];
     __shared__ double s_uj[MAX_ELL][AT];
     __shared__ __align__(16) double s_tile[AT][AT_PAD];
-    __shared__ double s_scal[3];       // sf2, Sii, jitter
+    __shared__ double s_scal[4];       // sf2, Sii (or 1 with GPMC_ASM_PRED), jitter, sn2 (GPMC_ASM_PRED)
 
     const double *h = hyp + (size_t)m * P;
     const int tid = threadIdx.x;
@@ -66,6 +66,12 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
         s_scal[0] = sf2;
         s_scal[1] = (flags & GPMC_ASM_ADD_S) ? Sii : 0.0;
         s_scal[2] = jitter ? jitter[m] : 0.0;
+        if (flags & GPMC_ASM_PRED) {
+            // inf_mcmc (sliceSample.py:256-257): sn2 = likfunc.sn**2 with likfunc.sn = exp(log_sigma); K/sn2 + eye(n)
+            const double snl = exp(log(sn));
+            s_scal[3] = snl * snl;
+            s_scal[1] = 1.0;
+        } else s_scal[3] = 1.0;
     }
     __syncthreads();
     // u = x / ell for the tile's rows and columns
@@ -82,7 +88,8 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
 
     const int warp = tid >> 5, lane = tid & 31;
     const double sf2 = s_scal[0];
-    const double diag_add = s_scal[1], jit = s_scal[2];
+    const double diag_add = s_scal[1], jit = s_scal[2], sn2 = s_scal[3];
+    const bool pred = (flags & GPMC_ASM_PRED) != 0;
     const bool has_jit = (jitter != nullptr);
     double *Ab = A.base + (size_t)m * A.stride;
     const int cl = 2 * lane;
@@ -107,8 +114,9 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
                 s0 = __dadd_rn(s0, __dmul_rn(d0, d0));
                 s1 = __dadd_rn(s1, __dmul_rn(d1, d1));
             }
-            const double k0 = sf2 * exp(-0.5 * s0);
-            const double k1 = sf2 * exp(-0.5 * s1);
+            double k0 = sf2 * exp(-0.5 * s0);
+            double k1 = sf2 * exp(-0.5 * s1);
+            if (pred) { k0 = k0 / sn2; k1 = k1 / sn2; }
             if (mirror) *reinterpret_cast<double2 *>(&s_tile[rl][cl]) = make_double2(k0, k1);
             *reinterpret_cast<double2 *>(dst + (size_t)rr * A.ld) = make_double2(k0, k1);
         }
@@ -127,6 +135,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
         }
         double k0 = sf2 * exp(-0.5 * s0);
         double k1 = sf2 * exp(-0.5 * s1);
+        if (pred) { k0 = k0 / sn2; k1 = k1 / sn2; }
         if (gr == gc)     { k0 = k0 + diag_add; if (has_jit) k0 = k0 + jit; }
         if (gr == gc + 1) { k1 = k1 + diag_add; if (has_jit) k1 = k1 + jit; }
         if (mirror) *reinterpret_cast<double2 *>(&s_tile[rl][cl]) = make_double2(k0, k1);

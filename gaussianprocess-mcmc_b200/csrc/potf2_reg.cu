@@ -1,15 +1,18 @@
 // Panel factor kernel, third form: the 128x128 diagonal block lives in REGISTERS as 8x8 DMMA accumulator fragments
 // spread over 8 warps, and is factored right-looking in 16 steps of 8 columns.  Used wherever potf2_lite.cu was
 // (kcGP.tools.jitchol call sites sliceSample.py:196,205): same inputs, same outputs (L11 in place, the sixteen 8x8
-// diagonal inverses in W, LAPACK-style info), about a quarter of its latency.
+// diagonal inverses in W, LAPACK-style info).
 //
 // Why: potf2_lite spends 42 % of its time in ONE warp that walks the 32 columns of a 32x32 sub-block with a row per
 // lane (ncu stall sampling, round 1) while the other warps wait, and stages the block through 90 KB of shared memory.
-// Here the sequential part shrinks to an 8x8 factorisation per step (one warp, row per lane, ~1000 cycles), and
-// everything else is DMMA work on register-resident fragments:
+// Here the sequential part shrinks to an 8x8 factorisation per step, and everything else is DMMA work on
+// register-resident fragments:
 //
 //   step b = 0..15  (block column b of 8x8 fragments)
-//     A  the warp that owns fragment (b,b) factors it:  L8 (and W8 = L8^-1) -> shared memory and global memory
+//     A  the warp that owns fragment (b,b) factors it together with its inverse: the 8 rows of the fragment and the 8
+//        rows of an identity ride in lanes 0-7 and 8-15 of ONE instruction stream (the elimination applies the same
+//        row operation to both), the next pivot is computed and broadcast before anything else (it is the critical
+//        path of the whole kernel) and its reciprocal square root is MUFU.RSQ64H + two Newton steps
 //     B  owners of fragments (r,b), r > b:  X = A W8^T, r = A - X L8^T, X += r W8^T  (inverse-multiply + one step of
 //        iterative refinement, the scheme of trsm_panel8.cu) -> global memory and the shared panel buffer
 //     C  every fragment (r,c), c > b:  acc -= X_r X_c^T   (2 DMMAs; X_r is the owner's own register pair -- with the
@@ -19,16 +22,19 @@
 //   others finish their updates.
 //
 // Ownership: warp w holds block rows w and 15-w = 17 fragments = 34 doubles per lane, in slots with COMPILE-TIME
-// register indices (slot s <= w: fragment (w, s); slot s > w: fragment (15-w, s-w-1)); which fragment a slot holds is
-// a warp-uniform runtime value, so each step walks the 17 slots with warp-uniform predicates.  Shared memory: 10 KB;
-// registers bound the occupancy at two CTAs (two matrices) per SM, which hides one CTA's single-warp phase A behind
-// the other's DMMA phases.
+// register indices, ordered by block column (slot 2c / 2c+1 = column c of row w / row 15-w while c <= w, then the
+// remaining columns of row 15-w).  With that order the fragments still alive at step b (column > b) are a SUFFIX of
+// the slot list, so phase C is one computed jump into a straight-line sequence of 17 slot updates -- no per-slot
+// predicates (the first version walked all 17 slots with warp-uniform tests in phases B and C: 3400 warp instructions
+// per step, ncu r02c) -- and phase B picks its (at most two) fragments with a 17-way switch.
+// Shared memory: 10 KB; registers bound the occupancy at two CTAs (two matrices) per SM, which hides one CTA's
+// single-warp phase A behind the other's DMMA phases.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
 namespace gpmc {
 
-static_assert(NB == 128 || NB == 64, "potf2_reg: panel width 64 or 128");
+static_assert(NB == 128, "potf2_reg is written for a panel width of 128 (16 x 16 fragments, 8 warps)");
 constexpr int PR_NF = NB / 8;                 // 8x8 fragments per block row / column (16)
 constexpr int PR_WARPS = PR_NF / 2;           // 8 warps: warp w owns block rows w and PR_NF-1-w
 constexpr int PR_THREADS = PR_WARPS * 32;
@@ -57,6 +63,40 @@ __device__ __forceinline__ double pivot_rsqrt(double a)
     return y;
 }
 
+// slot -> (block row, block column) of warp w (see the header comment)
+__device__ __forceinline__ void slot_rc(int s, int w, int &R, int &C, bool &isA)
+{
+    if (s < 2 * (w + 1)) { C = s >> 1; isA = (s & 1) == 0; }
+    else { C = s - w - 1; isA = false; }
+    R = isA ? w : PR_NF - 1 - w;
+}
+
+// phase C for one slot: acc -= X_R X_C^T
+template <int S>
+__device__ __forceinline__ void slot_update(double (&acc)[PR_SLOTS][2], int w, double xa0, double xa1, double xb0, double xb1,
+                                            const double (*sX)[64], int frag_off)
+{
+    int R, C; bool isA;
+    slot_rc(S, w, R, C, isA);
+    const double n0 = isA ? -xa0 : -xb0, n1 = isA ? -xa1 : -xb1;
+    double2 xc;
+    if (C == R) xc = make_double2(-n0, -n1);                              // diagonal fragment: X_C is this warp's own pair
+    else xc = *reinterpret_cast<const double2 *>(&sX[C][frag_off]);
+    dmma884_r(acc[S][0], acc[S][1], n0, xc.x);
+    dmma884_r(acc[S][0], acc[S][1], n1, xc.y);
+}
+
+#define PR_CASE(S) case S: slot_update<S>(acc, w, xa0, xa1, xb0, xb1, sX, frag_off);
+#define PR_PICK(S) case S: p0 = acc[S][0]; p1 = acc[S][1]; break;
+#define PR_PICK_ALL PR_PICK(0) PR_PICK(1) PR_PICK(2) PR_PICK(3) PR_PICK(4) PR_PICK(5) PR_PICK(6) PR_PICK(7) PR_PICK(8) \
+    PR_PICK(9) PR_PICK(10) PR_PICK(11) PR_PICK(12) PR_PICK(13) PR_PICK(14) PR_PICK(15) PR_PICK(16)
+
+__device__ __forceinline__ void pick_slot(const double (&acc)[PR_SLOTS][2], int slot, double &p0, double &p1)
+{
+    p0 = p1 = 0.0;
+    switch (slot) { PR_PICK_ALL default: break; }
+}
+
 __global__ void __launch_bounds__(PR_THREADS, 2)
 potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info, int zero_upper)
 {
@@ -73,6 +113,7 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     const int nv = min(NB, n - j0);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
+    const int frag_off = fr * 8 + 2 * fk;
     const int rowA = w, rowB = PR_NF - 1 - w;
 
     if (tid == 0) s_fail = 0;
@@ -80,8 +121,8 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     double acc[PR_SLOTS][2];
 #pragma unroll
     for (int s = 0; s < PR_SLOTS; ++s) {
-        const int R = (s <= w) ? rowA : rowB;
-        const int C = (s <= w) ? s : s - w - 1;
+        int R, C; bool isA;
+        slot_rc(s, w, R, C, isA);
         const int gr = R * 8 + fr, gc = C * 8 + 2 * fk;
         double2 v = make_double2(0.0, 0.0);
         if (gr < nv && gc < nv) v = *reinterpret_cast<const double2 *>(Ab + (size_t)gr * ld + gc);
@@ -98,78 +139,94 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
         // ------------------------------------------------------------------ A: 8x8 diagonal fragment, one warp
         const bool own_diag = (b < PR_WARPS) ? (w == b) : (w == PR_NF - 1 - b);
         if (own_diag) {
-            const int dslot = (b < PR_WARPS) ? b : PR_SLOTS - 1;
-#pragma unroll
-            for (int s = 0; s < PR_SLOTS; ++s)
-                if (s == dslot) *reinterpret_cast<double2 *>(&sD[fr * 8 + 2 * fk]) = make_double2(acc[s][0], acc[s][1]);
+            double d0, d1;
+            pick_slot(acc, (b < PR_WARPS) ? 2 * b : PR_SLOTS - 1, d0, d1);
+            *reinterpret_cast<double2 *>(&sD[frag_off]) = make_double2(d0, d1);
             __syncwarp();
-            // row (lane & 7) per lane; the four replicas compute the same thing, so every shuffle source is valid
-            const int r8 = lane & 7;
-            double a[8], x[8];
+            // lanes 0-7: row (lane) of the fragment; lanes 8-15: row (lane - 8) of an identity -- eliminating [A; I] gives
+            // [L; W^T] column by column: lane 8 + k ends with column k of W8 = L8^-1.  Lanes 16-31 repeat lanes 0-15.
+            const int l16 = lane & 15, r8 = lane & 7;
+            double v[8];
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(&sD[r8 * 8 + c]);
-                a[c] = (c <= r8) ? v.x : 0.0;
-                a[c + 1] = (c + 1 <= r8) ? v.y : 0.0;
+                const double2 t = *reinterpret_cast<const double2 *>(&sD[r8 * 8 + c]);
+                v[c] = (l16 < 8) ? ((c <= r8) ? t.x : 0.0) : ((c == r8) ? 1.0 : 0.0);
+                v[c + 1] = (l16 < 8) ? ((c + 1 <= r8) ? t.y : 0.0) : ((c + 1 == r8) ? 1.0 : 0.0);
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[c] = (c == r8) ? 1.0 : 0.0;
             int fail = 0;
-            double piv = __shfl_sync(0xffffffffu, a[0], 0);
+            double piv = __shfl_sync(0xffffffffu, v[0], 0);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (!(piv > 0.0) && fail == 0) fail = j0 + b * 8 + c + 1;           // dpotf2: ajj <= 0 or NaN
                 const double rinv = pivot_rsqrt(piv);
-                a[c] = (r8 == c) ? piv * rinv : a[c] * rinv;
-                x[c] = x[c] * rinv;
+                v[c] = v[c] * rinv;                                                 // lane c: piv * rinv = sqrt(piv)
                 if (c < 7) {
-                    // the next pivot first (it is the critical path of the whole kernel): row c+1 holds both a[c+1] and its
-                    // own multiplier l_{c+1,c}, so the value needs no shuffle before it is broadcast
-                    piv = __shfl_sync(0xffffffffu, fma(-a[c], a[c], a[c + 1]), c + 1);
+                    // the next pivot first: row c+1 holds both its diagonal entry and its own multiplier l_{c+1,c}, so
+                    // the value needs no shuffle before it is broadcast
+                    piv = __shfl_sync(0xffffffffu, fma(-v[c], v[c], v[c + 1]), c + 1);
                 }
 #pragma unroll
                 for (int j = c + 1; j < 8; ++j) {
-                    const double ljc = __shfl_sync(0xffffffffu, a[c], j);
-                    a[j] = fma(-a[c], ljc, a[j]);
-                    x[j] = fma(-x[c], ljc, x[j]);                                   // lane k ends with column k of L8^-1
+                    const double ljc = __shfl_sync(0xffffffffu, v[c], j);           // l_{j,c} from row j of the fragment
+                    v[j] = fma(-v[c], ljc, v[j]);
                 }
             }
             if (lane < 8) {
                 const int gr = b * 8 + r8;
 #pragma unroll
                 for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2 *>(&sL8[r8 * 8 + c]) = make_double2((c <= r8) ? a[c] : 0.0, (c + 1 <= r8) ? a[c + 1] : 0.0);
+                    *reinterpret_cast<double2 *>(&sL8[r8 * 8 + c]) = make_double2((c <= r8) ? v[c] : 0.0, (c + 1 <= r8) ? v[c + 1] : 0.0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c <= r8 && gr < nv) Ab[(size_t)gr * ld + b * 8 + c] = v[c];
+                if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;           // the FIRST failing pivot (later ones are NaN)
+            } else if (lane < 16) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    sW8[c * 8 + r8] = x[c];                                         // W8[c][k = r8]; zero for c < k
-                    Wb[(size_t)(b * 8 + c) * NB + b * 8 + r8] = x[c];
-                    if (c <= r8 && gr < nv) Ab[(size_t)gr * ld + b * 8 + c] = a[c];
+                    sW8[c * 8 + r8] = v[c];                                         // W8[c][k = r8]; zero for c < k
+                    Wb[(size_t)(b * 8 + c) * NB + b * 8 + r8] = v[c];
                 }
-                if (fail != 0 && lane == 0 && s_fail == 0) s_fail = fail;           // the FIRST failing pivot (later ones are NaN)
             }
         }
         __syncthreads();
-        // ------------------------------------------------------------------ B: fragments (r, b), r > b
+        // ------------------------------------------------------------------ B: fragments (r, b), r > b (at most two per warp)
         {
-            const double2 wv = *reinterpret_cast<const double2 *>(&sW8[fr * 8 + 2 * fk]);
-            const double2 lv = *reinterpret_cast<const double2 *>(&sL8[fr * 8 + 2 * fk]);
-#pragma unroll
-            for (int s = 0; s < PR_SLOTS; ++s) {
-                const bool isA = (s <= w);
-                const int R = isA ? rowA : rowB;
-                const int C = isA ? s : s - w - 1;
-                if (C == b && R > b) {
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma884_r(x0, x1, acc[s][0], wv.x);                             // X0 = A W8^T
-                    dmma884_r(x0, x1, acc[s][1], wv.y);
-                    double r0 = acc[s][0], r1 = acc[s][1];
-                    dmma884_r(r0, r1, -x0, lv.x);                                   // r = A - X0 L8^T
-                    dmma884_r(r0, r1, -x1, lv.y);
-                    dmma884_r(x0, x1, r0, wv.x);                                    // X = X0 + r W8^T
-                    dmma884_r(x0, x1, r1, wv.y);
-                    *reinterpret_cast<double2 *>(&sX[R][fr * 8 + 2 * fk]) = make_double2(x0, x1);
-                    if (isA) { xa0 = x0; xa1 = x1; } else { xb0 = x0; xb1 = x1; }
-                    const int gr = R * 8 + fr, gc = b * 8 + 2 * fk;
+            // slot of (rowA, b): 2b while b < w;  slot of (rowB, b): 2b+1 while b <= w, then w+1+b while b < rowB
+            const int slotA = (b < w) ? 2 * b : -1;
+            const int slotB = (b <= w) ? 2 * b + 1 : ((b < rowB) ? w + 1 + b : -1);
+            if (slotB >= 0) {
+                const double2 wv = *reinterpret_cast<const double2 *>(&sW8[frag_off]);
+                const double2 lv = *reinterpret_cast<const double2 *>(&sL8[frag_off]);
+                double a0, a1, b0, b1;
+                pick_slot(acc, slotA, a0, a1);                                      // zeros when the warp has no row-A fragment here
+                pick_slot(acc, slotB, b0, b1);
+                double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+                dmma884_r(x0, x1, a0, wv.x);                                        // X0 = A W8^T   (two independent chains)
+                dmma884_r(y0, y1, b0, wv.x);
+                dmma884_r(x0, x1, a1, wv.y);
+                dmma884_r(y0, y1, b1, wv.y);
+                double r0 = a0, r1 = a1, q0 = b0, q1 = b1;
+                dmma884_r(r0, r1, -x0, lv.x);                                       // r = A - X0 L8^T
+                dmma884_r(q0, q1, -y0, lv.x);
+                dmma884_r(r0, r1, -x1, lv.y);
+                dmma884_r(q0, q1, -y1, lv.y);
+                dmma884_r(x0, x1, r0, wv.x);                                        // X = X0 + r W8^T
+                dmma884_r(y0, y1, q0, wv.x);
+                dmma884_r(x0, x1, r1, wv.y);
+                dmma884_r(y0, y1, q1, wv.y);
+                xb0 = y0; xb1 = y1;
+                *reinterpret_cast<double2 *>(&sX[rowB][frag_off]) = make_double2(y0, y1);
+                {
+                    const int gr = rowB * 8 + fr, gc = b * 8 + 2 * fk;
+                    if (gr < nv) {
+                        if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(y0, y1);
+                        else if (gc < nv) Ab[(size_t)gr * ld + gc] = y0;
+                    }
+                }
+                if (slotA >= 0) {
+                    xa0 = x0; xa1 = x1;
+                    *reinterpret_cast<double2 *>(&sX[rowA][frag_off]) = make_double2(x0, x1);
+                    const int gr = rowA * 8 + fr, gc = b * 8 + 2 * fk;
                     if (gr < nv) {
                         if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(x0, x1);
                         else if (gc < nv) Ab[(size_t)gr * ld + gc] = x0;
@@ -178,19 +235,13 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
             }
         }
         __syncthreads();
-        // ------------------------------------------------------------------ C: fragments (r, c), c > b
-#pragma unroll
-        for (int s = 0; s < PR_SLOTS; ++s) {
-            const bool isA = (s <= w);
-            const int R = isA ? rowA : rowB;
-            const int C = isA ? s : s - w - 1;
-            if (C > b) {
-                const double n0 = isA ? -xa0 : -xb0, n1 = isA ? -xa1 : -xb1;
-                double2 xc;
-                if (C == R) xc = make_double2(-n0, -n1);                            // diagonal fragment: X_c is this warp's own pair
-                else xc = *reinterpret_cast<const double2 *>(&sX[C][fr * 8 + 2 * fk]);
-                dmma884_r(acc[s][0], acc[s][1], n0, xc.x);
-                dmma884_r(acc[s][0], acc[s][1], n1, xc.y);
+        // ------------------------------------------------------------------ C: fragments (r, c), c > b: a suffix of the slots
+        {
+            const int start = (b + 1 <= w) ? 2 * (b + 1) : w + b + 2;
+            switch (start) {
+                PR_CASE(0) PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7) PR_CASE(8)
+                PR_CASE(9) PR_CASE(10) PR_CASE(11) PR_CASE(12) PR_CASE(13) PR_CASE(14) PR_CASE(15) PR_CASE(16)
+                default: break;
             }
         }
     }

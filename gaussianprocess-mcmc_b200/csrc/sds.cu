@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
         gid = st.chain_of[c];
     }
     const int P = st.P, n = st.n;
+    const unsigned sweep = st.iter_of ? (unsigned)st.iter_of[c] : st.sweep;
     __shared__ double s_S;
     if (st.chain_of) {
         // the chain's current state comes straight from the caller's arrays into the slot rows
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
         for (int p = 0; p < P; ++p) {
             double u;
             if (st.tape_v) u = st.tape_v[(size_t)gid * P + p];
-            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_BRACKET, p, u, u1); }
+            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, sweep, STREAM_BRACKET, p, u, u1); }
             const double v = 0.0 + (st.scale[p] - 0.0) * u;
             const double lo = fmax(hyp[p] - v, 0.0);
             st.hyp_min[(size_t)c * P + p] = lo;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
         }
         double u0;
         if (st.tape_u0) u0 = st.tape_u0[gid];
-        else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_BRACKET, 1000, u0, u1); }
+        else { double u1; philox_uniform2(st.seed, st.chain0 + gid, sweep, STREAM_BRACKET, 1000, u0, u1); }
         st.log_u0[c] = log(u0);
         st.done[c] = 0;
         st.ntrips[c] = 0;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) sds_begin_kernel(SdsState st)
         if (st.tape_z) z = st.tape_z[(size_t)gid * n + i];
         else {
             double u0, u1;
-            philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_Z, i >> 1, u0, u1);
+            philox_uniform2(st.seed, st.chain0 + gid, sweep, STREAM_Z, i >> 1, u0, u1);
             const double rad = sqrt(-2.0 * log(u0));
             z = (i & 1) ? rad * sin(6.283185307179586 * u1) : rad * cos(6.283185307179586 * u1);
         }
@@ -153,11 +154,12 @@ __global__ void __launch_bounds__(256) sds_threshold_kernel(SdsState st)
     const double llk = tg2_loglik_block(st.y, st.my, st.F + (size_t)c * st.ldv, st.n, sn0, st.lower, st.upper, red);   // :118
     if (threadIdx.x == 0) {
         st.cur_llk[c] = llk;
-        st.threshold[c] = density_sum(st.log_u0[c] + llk, hyp, st.prior_k, st.prior_theta, P, st.G[c], st.iter);       // :127-129
+        const int it = st.iter_of ? st.iter_of[c] : st.iter;
+        st.threshold[c] = density_sum(st.log_u0[c] + llk, hyp, st.prior_k, st.prior_theta, P, st.G[c], it);            // :127-129
         st.curG[c] = st.G[c];
         if (st.chain_of) {
             st.phase[c] = SDS_PHASE_ACTIVE;
-            if (st.loglik_glob) st.loglik_glob[gid] = st.G[c];     // what a chain that never accepts reports
+            if (st.loglik_glob && !st.iter_of) st.loglik_glob[gid] = st.G[c];     // what a chain that never accepts reports
         }
     }
 }
@@ -176,17 +178,18 @@ __global__ void __launch_bounds__(256) sds_propose_kernel(SdsState st, int trip)
         gid = c;
     }
     const int P = st.P;
+    const int it = st.iter_of ? st.iter_of[c] : st.iter;
     __shared__ double s_S;
     if (threadIdx.x == 0) {
         double *th = st.theta + (size_t)c * P;
         for (int p = 0; p < P; ++p) {
             double u;
             if (st.tape_U) u = st.tape_U[((size_t)gid * st.tape_trips + trip) * P + p];
-            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, st.sweep, STREAM_TRIP, trip * 64 + p, u, u1); }
+            else { double u1; philox_uniform2(st.seed, st.chain0 + gid, (unsigned)it, STREAM_TRIP, trip * 64 + p, u, u1); }
             const double lo = st.hyp_min[(size_t)c * P + p], hi = st.hyp_max[(size_t)c * P + p];
             th[p] = lo + (hi - lo) * u;                                                 // :132
         }
-        if (st.iter < 500) th[P - 1] = st.hyp[(size_t)c * P + P - 1];                  // :133-134
+        if (it < 500) th[P - 1] = st.hyp[(size_t)c * P + P - 1];                       // :133-134
         s_S = s_diag_value(th[P - 2], th[P - 1]);
         if (st.chain_of) st.resolved[c] = 0;
     }
@@ -209,24 +212,25 @@ __global__ void __launch_bounds__(256) sds_accept_kernel(SdsState st)
         gid = c;
     }
     __shared__ double red[8];
-    __shared__ int s_accept;
+    __shared__ int s_accept, s_finished;
     const int P = st.P;
     const double *th = st.theta + (size_t)c * P;
     const double *fp = st.fprop + (size_t)c * st.ldv;
-    const double llk = tg2_loglik_block(st.y, st.my, fp, st.n, th[P - 1], st.lower, st.upper, red);                   // :142-143
+    const int it = st.iter_of ? st.iter_of[c] : st.iter;          // (read before the block barriers inside tg2_loglik_block:
+    const double llk = tg2_loglik_block(st.y, st.my, fp, st.n, th[P - 1], st.lower, st.upper, red);   // thread 0 advances it below)  :142-143
     if (threadIdx.x == 0) {
-        const double proposal = density_sum(llk, th, st.prior_k, st.prior_theta, P, st.G[c], st.iter);                // :149-152
+        const double proposal = density_sum(llk, th, st.prior_k, st.prior_theta, P, st.G[c], it);                     // :149-152
         const bool ok = (proposal > st.threshold[c]) && isfinite(proposal);                                         // :154
         st.ntrips[c] += 1;
         st.last_proposal[c] = proposal;
         st.last_llk[c] = llk;
+        bool finished = ok;                                // this transition is over (accepted, or out of trips)
         if (ok) {
-            st.done[c] = 1;
             if (st.chain_of) {
                 for (int p = 0; p < P; ++p) st.hyp_glob_out[(size_t)gid * P + p] = th[p];
                 if (st.loglik_glob) st.loglik_glob[gid] = st.G[c];
                 if (st.ntrips_glob) st.ntrips_glob[gid] = st.ntrips[c];
-                if (st.status_glob) st.status_glob[gid] = 0;
+                if (st.status_glob && !st.iter_of) st.status_glob[gid] = 0;
             } else {
                 for (int p = 0; p < P; ++p) st.hyp_out[(size_t)c * P + p] = th[p];
                 st.loglik_out[c] = st.G[c];
@@ -239,12 +243,27 @@ __global__ void __launch_bounds__(256) sds_accept_kernel(SdsState st)
             }
             if (st.chain_of && st.ntrips[c] >= st.max_trips) {
                 // the trip budget ran out (the reference's `while True` would go on): the chain keeps its state
-                st.done[c] = 1;
+                finished = true;
                 if (st.ntrips_glob) st.ntrips_glob[gid] = st.ntrips[c];
                 if (st.status_glob) st.status_glob[gid] = 1;
+                if (st.n_exhausted) atomicAdd(st.n_exhausted, 1);
             }
         }
+        if (finished) {
+            if (st.iter_of) {
+                // many iterations per call: record the sample, then either start the chain's next transition in this slot
+                // (the state it reads back is the one just written) or free the slot
+                const int k = it - st.iter;
+                const double *hrec = ok ? th : st.hyp + (size_t)c * P;
+                if (st.hist_hyp) for (int p = 0; p < P; ++p) st.hist_hyp[((size_t)gid * st.n_iters + k) * P + p] = hrec[p];
+                if (st.hist_loglik) st.hist_loglik[(size_t)gid * st.n_iters + k] = ok ? st.G[c] : st.curG[c];
+                if (st.hist_trips) st.hist_trips[(size_t)gid * st.n_iters + k] = st.ntrips[c];
+                if (k + 1 < st.n_iters) { st.iter_of[c] = it + 1; st.phase[c] = SDS_PHASE_NEW; }
+                else st.done[c] = 1;
+            } else st.done[c] = 1;
+        }
         s_accept = ok ? 1 : 0;
+        s_finished = finished ? 1 : 0;
     }
     __syncthreads();
     if (s_accept) {
@@ -254,6 +273,14 @@ __global__ void __launch_bounds__(256) sds_accept_kernel(SdsState st)
         } else {
             double *fo = st.F_out + (size_t)c * st.ldv;
             for (int i = threadIdx.x; i < st.n; i += blockDim.x) fo[i] = fp[i];                                     // :156
+        }
+    }
+    if (s_finished && st.iter_of && st.hist_f) {
+        const int k = it - st.iter;
+        if (st.thin > 0 && (k % st.thin) == 0 && k / st.thin < st.n_keep) {
+            const double *src = s_accept ? fp : st.F + (size_t)c * st.ldv;        // accepted f', or the unchanged f
+            double *dst = st.hist_f + ((size_t)gid * st.n_keep + k / st.thin) * st.n;
+            for (int i = threadIdx.x; i < st.n; i += blockDim.x) dst[i] = src[i];
         }
     }
 }
@@ -316,7 +343,10 @@ __global__ void __launch_bounds__(1024) sds_admit_kernel(SdsState st, int round)
         const int next = s_next;
         if (is_free) {
             const int id = next + rank;
-            if (id < st.n_chains) { st.chain_of[c] = id; st.phase[c] = SDS_PHASE_NEW; st.parked[c] = 0; st.resolved[c] = 0; st.ntrips[c] = 0; }
+            if (id < st.n_chains) {
+                st.chain_of[c] = id; st.phase[c] = SDS_PHASE_NEW; st.parked[c] = 0; st.resolved[c] = 0; st.ntrips[c] = 0;
+                if (st.iter_of) st.iter_of[c] = st.iter;
+            }
             else { st.chain_of[c] = -1; st.phase[c] = SDS_PHASE_FREE; }
             st.done[c] = 0;
         }

@@ -48,6 +48,16 @@ struct SdsState {
     double *loglik_glob;           // [n_chains] (may be nullptr)
     double *hyp_stage;             // [cap, P] slot copy of the chain's current theta (== hyp on this path)
     double *F_stage;               // [cap, ldv] slot copy of the chain's current f (== F on this path)
+    // ---- many iterations per call (gpmc_sds_run): a slot keeps its chain from iteration iter to iter + n_iters - 1, every
+    // chain advances on its own (no chain waits for the slowest one at an iteration boundary), history goes to hist_*.
+    int *iter_of;                  // [cap] MCMC iteration the slot's chain is at (nullptr: one transition per call, `iter`)
+    int n_iters;                   // iterations per chain in this call
+    double *hist_hyp;              // [n_chains, n_iters, P]   (may be nullptr)
+    double *hist_loglik;           // [n_chains, n_iters]      (may be nullptr)
+    int *hist_trips;               // [n_chains, n_iters]      (may be nullptr)
+    double *hist_f;                // [n_chains, n_keep, n], f after every thin-th iteration (may be nullptr)
+    int thin, n_keep;
+    int *n_exhausted;              // transitions that used up max_trips (state kept)
     // explicit randomness (all nullptr -> Philox)
     const double *tape_z;          // [B, n]
     const double *tape_v;          // [B, P]

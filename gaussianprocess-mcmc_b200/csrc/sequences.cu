@@ -169,8 +169,8 @@ void set_potrf_window(int w) { g_window_override = (w > 0 && w % NB == 0) ? w : 
 static int potrf_window_for(int n, int B)
 {
     const int nt = (n + 127) / 128;                 // 128-row tiles of a block column
+    if (g_window_override) return g_window_override >= n ? 0 : g_window_override;   // experiments: forced (>= n: plain left-looking)
     if ((long long)B * nt >= 1024) return 0;
-    if (g_window_override) return g_window_override;
     return n >= 8192 ? 1024 : 512;
 }
 
@@ -227,8 +227,12 @@ void set_lookahead_mode(int mode) { g_lookahead_mode = mode; }
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper_flag, cudaStream_t s, int border_rows)
 {
-    if (border_rows < 0 || border_rows > 1) { set_error("potrf_sequence: at most one border row"); return GPMC_EINVAL; }
+    if (border_rows < 0) { set_error("potrf_sequence: border_rows < 0"); return GPMC_EINVAL; }
     const int nr = n + border_rows;                     // rows that take part in the panel solves
+    // ONE border row is carried by the idle diagonal warp of the update kernel (border duty); several of them (the
+    // right-hand sides of the predictive path) are simply more rows below the matrix for the update GEMM
+    const int xrows = border_rows > 1 ? border_rows : 0;
+    const int brow = border_rows == 1 ? n : 0;
     // w_step != 0: the caller keeps every diagonal-block inverse for inverse_sequence -> full inverse needed
     // The lite kernel emits the 8x8 diagonal inverses only: enough for trsm_panel8 (not for trsm_panel's 32x32 blocks).
     // Measured: it is the faster of the two at every batch size.  Callers that keep the block inverses (w_step != 0)
@@ -247,11 +251,22 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     auto update = [&](int j0, int width, int k_begin, int k_end, cudaStream_t st) -> int {
         GemmArgs g{};
         g.C = A; g.A = self; g.B = self;
-        g.cr0 = j0; g.cc0 = j0; g.rows = n - j0; g.cols = width;
-        g.border_row = border_rows ? n : 0;
+        g.cr0 = j0; g.cc0 = j0; g.rows = n - j0 + xrows; g.cols = width;
+        g.border_row = brow;
         g.ar0 = j0; g.br0 = j0; g.k0 = k_begin; g.bk0 = k_begin; g.klen = k_end - k_begin;
         g.epi = EPI_SUB;
         g.skip_upper = 1;                               // potf2 reads the lower triangle of the diagonal block only
+        return launch_gemm(g, B, KC_GEMM, st);
+    };
+
+    // several border rows under a SQUARE (lower-only) trailing update: one more, rectangular, launch for those rows
+    auto extra_rows_update = [&](int c0, int cols, int k_begin, int klen, cudaStream_t st) -> int {
+        if (xrows == 0 || cols <= 0) return 0;
+        GemmArgs g{};
+        g.C = A; g.A = self; g.B = self;
+        g.cr0 = n; g.cc0 = c0; g.rows = xrows; g.cols = cols;
+        g.ar0 = n; g.br0 = c0; g.k0 = k_begin; g.bk0 = k_begin; g.klen = klen;
+        g.epi = EPI_SUB;
         return launch_gemm(g, B, KC_GEMM, st);
     };
 
@@ -265,13 +280,14 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 GemmArgs g{};
                 g.C = A; g.A = self; g.B = self;
                 g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = n - w1;
-                g.border_row = border_rows ? n : 0;
+                g.border_row = brow;
                 g.ar0 = w1; g.br0 = w1; g.k0 = w0 - wlen; g.bk0 = w0 - wlen; g.klen = wlen;
                 g.lower_only = 1;
                 g.epi = EPI_SUB;
                 g.skip_upper = 1;
                 int rc = launch_gemm(g, B, KC_GEMM, sG);
                 if (rc) return rc;
+                if ((rc = extra_rows_update(w1, n - w1, w0 - wlen, wlen, sG))) return rc;
             }
         }
         for (int j0 = w0; j0 < w1; j0 += NB) {
@@ -295,6 +311,9 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             if (rc) return rc;
             if (j0 + NB < n && (rc = (g_trsm_mode == 1 ? launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP)
                                                         : launch_trsm_panel8(A, nr, j0, Wj, strideW, B, sP)))) return rc;
+            // several border rows: the last block column is solved for them here too (a single border row is finished by
+            // border_finish together with the quadratic form)
+            if (j0 + NB >= n && xrows > 0 && (rc = launch_trsm_panel8(A, nr, j0, Wj, strideW, B, sP, n, n))) return rc;
             if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
         }
         if (la) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sG, la->ev_p, 0));                            // join
@@ -303,14 +322,15 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
             const int w2 = std::min(n, w1 + wlen);
             GemmArgs g{};
             g.C = A; g.A = self; g.B = self;
-            g.cr0 = w1; g.cc0 = w1; g.rows = n - w1; g.cols = split ? w2 - w1 : n - w1;
-            g.border_row = border_rows ? n : 0;
+            g.cr0 = w1; g.cc0 = w1; g.rows = n - w1 + (split ? xrows : 0); g.cols = split ? w2 - w1 : n - w1;
+            g.border_row = brow;
             g.ar0 = w1; g.br0 = w1; g.k0 = w0; g.bk0 = w0; g.klen = w1 - w0;
             g.lower_only = split ? 0 : 1;               // split: the next window's columns first (rectangular, the tiles
             g.epi = EPI_SUB;                            // above the diagonal exit at once), the rest at the top of the loop
             g.skip_upper = 1;
             int rc = launch_gemm(g, B, KC_GEMM, sG);
             if (rc) return rc;
+            if (!split && (rc = extra_rows_update(w1, n - w1, w0, w1 - w0, sG))) return rc;
         }
     }
     if (zero_upper_flag) return zero_upper(A, n, B, s);

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <functional>
+
 namespace gpmc {
 
 // Left-looking blocked Cholesky of every item of A (lower, in place).  The inverse of diagonal block j is
@@ -14,6 +16,12 @@ namespace gpmc {
 // substitution: chol([[A, g], [g^T, c]]) has (L^-1 g)^T as its last row); border_finish() completes the last block.
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper, cudaStream_t s, int border_rows = 0);
+
+// One wave of assemble-and-factor with the pyGPs jitter ladder (capi.cu); shared by the log-lik unit, the predictive
+// path and the elliptical slice sampler's Cholesky draw.
+int factor_wave(const std::function<int(BatchView, int, const double *)> &fill, const std::function<double(const double *)> &diag_value,
+                BatchView A, int N, int nb, const double *hyp_w, int P, int *info_w, double *W, double *jit_dev, int *map_dev,
+                int jitter_policy, int border_rows, cudaStream_t s);
 
 // Write rhs[item] (length n, row stride ldv) into border row n of every item (zero padded up to ld).
 int border_set(BatchView A, int n, const double *rhs, int ldv, int B, cudaStream_t s);

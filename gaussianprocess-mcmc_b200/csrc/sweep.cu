@@ -34,7 +34,7 @@ struct SweepBuffers {
     double *theta, *hyp_min, *hyp_max, *hyp_in, *hyp_out;         // [cap, P]
     double *G, *log_u0, *threshold, *cur_llk, *curG, *last_prop, *last_llk, *jit, *mean, *loglik_out;   // [cap]
     int *done, *ntrips, *map, *count, *info1, *info2, *bad, *fmap;   // ints
-    int *chain_of, *phase, *parked, *resolved, *map_new, *map_act;   // resident loop (sds.cuh)
+    int *chain_of, *phase, *parked, *resolved, *map_new, *map_act, *iter_of;   // resident loop (sds.cuh)
     int *count_new, *count_act, *status_word, *next_chain;           // (inside the 256-byte block of `count`)
 };
 
@@ -59,7 +59,7 @@ static size_t layout(SweepBuffers &w, char *base, int n, int P, int cap)
     double **scal[] = {&w.G, &w.log_u0, &w.threshold, &w.cur_llk, &w.curG, &w.last_prop, &w.last_llk, &w.jit, &w.mean, &w.loglik_out};
     for (double **v : scal) *v = (double *)carve(p, (size_t)8 * cap);
     int **ints[] = {&w.done, &w.ntrips, &w.map, &w.info1, &w.info2, &w.bad, &w.fmap,
-                    &w.chain_of, &w.phase, &w.parked, &w.resolved, &w.map_new, &w.map_act};
+                    &w.chain_of, &w.phase, &w.parked, &w.resolved, &w.map_new, &w.map_act, &w.iter_of};
     for (int **v : ints) *v = (int *)carve(p, (size_t)4 * cap);
     w.count = (int *)carve(p, 256);                  // [0] count, [16] ladder scratch count, then the resident loop's words
     w.count_new = w.count + 24; w.count_act = w.count + 25; w.next_chain = w.count + 26; w.status_word = w.count + 32;
@@ -292,6 +292,14 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
 //   * a factorisation that fails parks its slot (no decision is taken for it); when the host sees parked slots in the
 //     status word it drains the stream and runs the pyGPs jitter ladder for those slots alone (aux_eval), then resumes.
 // Results are those of the wave loop bit for bit: randomness and tapes are keyed by the chain, not by the slot or round.
+// gpmc_sds_run: where the history of a multi-iteration call goes (all pointers may be nullptr)
+struct RunSpec {
+    int n_iters = 1;
+    double *hist_hyp = nullptr, *hist_loglik = nullptr, *hist_f = nullptr;
+    int *hist_trips = nullptr, *n_exhausted = nullptr;
+    int thin = 0, n_keep = 0;
+};
+
 struct ResidentHost {
     static constexpr int RING = 8;
     int *pinned = nullptr;                      // RING status words
@@ -331,7 +339,7 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
                               double my, double lower, double upper, unsigned long long seed, unsigned chain0,
                               const double *tape_z, const double *tape_v, const double *tape_u0, const double *tape_U, int tape_trips,
                               int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
-                              SweepBuffers &w, cudaStream_t s)
+                              SweepBuffers &w, cudaStream_t s, const RunSpec *run = nullptr)
 {
     ResidentHost *rh = resident_host();
     if (!rh) { set_error("sds_sweep: cannot allocate the pinned status ring"); return GPMC_ENOMEM; }
@@ -365,6 +373,13 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
     st.F_glob = F_dev; st.F_glob_out = F_dev; st.hyp_glob = hyp_dev; st.hyp_glob_out = hyp_dev;
     st.ntrips_glob = ntrips_dev; st.status_glob = status_dev; st.loglik_glob = loglik_dev;
     st.hyp_stage = w.hyp_in; st.F_stage = w.Fin;
+    if (run) {
+        // many iterations per call: `iter` is the first one, every slot carries its chain's own iteration
+        st.iter_of = w.iter_of; st.n_iters = run->n_iters;
+        st.hist_hyp = run->hist_hyp; st.hist_loglik = run->hist_loglik; st.hist_trips = run->hist_trips;
+        st.hist_f = run->hist_f; st.thin = run->thin; st.n_keep = run->n_keep; st.n_exhausted = run->n_exhausted;
+        if (run->n_exhausted) GPMC_CUDA_CHECK(cudaMemsetAsync(run->n_exhausted, 0, sizeof(int), s));
+    }
 
     const BatchView C2all{w.buf2, w.mat, w.ld, w.map, w.count};
     const BatchView C2new{w.buf2, w.mat, w.ld, w.map_new, w.count_new};
@@ -443,8 +458,9 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
             known_count = cap;                   // the parked slots are back in the lists
         }
         // ---- one round, sized by what the host knows
-        const int nb_new = std::min(cap, B - known_next);                    // chains that can still be admitted
         const int nb_all = known_next < B ? std::min(cap, B) : std::min(cap, known_count);
+        // new transitions this round: chains that can still be admitted -- or, with many iterations per call, any slot
+        const int nb_new = run ? nb_all : std::min(cap, B - known_next);
         const int nb_act = nb_all;
         if ((rc = launch_sds_admit(st, (int)round, s))) return rc;
         {
@@ -530,6 +546,40 @@ int gpmc_trsv_lower_batched(const double *L_dev, int N, int ld, long long stride
     BatchView Lv{const_cast<double *>(L_dev), strideL, ld, nullptr, nullptr};
     // quad_dev (optional) receives -(0.5 x.x + sum log L_ii + 0.5 N log 2pi), i.e. log N(b; 0, L L^T)
     return launch_solve_reduce(Lv, N, rhs_dev, nullptr, ldv, out_dev, quad_dev, nullptr, B, (cudaStream_t)stream);
+}
+
+int gpmc_sds_run(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, double *hyp_dev, int B, int P,
+                 int kind, const double *scale_dev, const double *prior_k_dev, const double *prior_theta_dev, int iter_begin, int n_iters,
+                 double my, double lower, double upper, unsigned long long seed, unsigned chain0, int max_trips, int jitter_policy,
+                 double *hist_hyp_dev, double *hist_loglik_dev, int *hist_trips_dev, double *hist_f_dev, int thin, int n_keep,
+                 int *n_exhausted_dev, void *ws_dev, size_t ws_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
+    if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2 || max_trips <= 0 || n_iters < 0 || (hist_f_dev && (thin <= 0 || n_keep <= 0))) {
+        set_error("sds_run: bad shape N=%d D=%d B=%d P=%d kind=%d max_trips=%d n_iters=%d thin=%d n_keep=%d", N, D, B, P, kind, max_trips,
+                  n_iters, thin, n_keep);
+        return GPMC_EINVAL;
+    }
+    if (B == 0 || n_iters == 0) return 0;
+    int cap = std::min(B, MAX_BATCH_ITEMS);
+    while (cap > 1 && sweep_bytes(N, P, cap) > ws_bytes) cap = (cap + 1) / 2;
+    if (!ws_dev || sweep_bytes(N, P, cap) > ws_bytes) {
+        set_error("sds_run: workspace %zu bytes cannot hold one chain (%zu needed)", ws_bytes, sweep_bytes(N, P, 1));
+        return GPMC_ENOMEM;
+    }
+    SweepBuffers w;
+    layout(w, (char *)ws_dev, N, P, cap);
+    if (w.ld != N) {
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
+    }
+    RunSpec run;
+    run.n_iters = n_iters; run.hist_hyp = hist_hyp_dev; run.hist_loglik = hist_loglik_dev; run.hist_trips = hist_trips_dev;
+    run.hist_f = hist_f_dev; run.thin = thin; run.n_keep = n_keep; run.n_exhausted = n_exhausted_dev;
+    return sds_sweep_resident(x_dev, y_dev, N, D, F_dev, hyp_dev, B, P, n_ell, scale_dev, prior_k_dev, prior_theta_dev, iter_begin,
+                              my, lower, upper, seed, chain0, nullptr, nullptr, nullptr, nullptr, 0, max_trips, jitter_policy,
+                              nullptr, nullptr, nullptr, w, s, &run);
 }
 
 size_t gpmc_sds_workspace_bytes(int N, int P, int chains_per_wave)

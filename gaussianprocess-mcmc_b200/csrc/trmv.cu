@@ -1,5 +1,6 @@
 // Triangular matrix-vector products of the SDS proposal (HBM-read bound, 8*n*(n+1)/2 bytes per item):
 //   mode 0, lower:  f' = C eta + m                         sliceSample.py:140  (np.dot(chol_R_theta, ita) + m_theta_g)
+//   mode 2, lower:  nu = L z                               sliceSample.py:41   (the Cholesky draw of elliptical_slice)
 //   mode 1, upper:  m  = g - S * (U z),  U = L^-T, z = L^-1 g   i.e.  m = R S^-1 g = g - S (K+S)^-1 g
 //                                                          sliceSample.py:204  (np.dot(np.dot(R_theta, inv(S)), g))
 // One warp per row, lanes stride the row with double2 loads (512 contiguous bytes per warp instruction);
@@ -44,7 +45,7 @@ trmv_kernel(BatchView T, int n, int upper, int mode, const double *__restrict__ 
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
             const size_t o = (size_t)m * ldv + r;
-            out[o] = (mode == 0) ? acc + add[o] : add[o] - svec[o] * acc;
+            out[o] = (mode == 0) ? acc + add[o] : (mode == 1 ? add[o] - svec[o] * acc : acc);
         }
     }
 }

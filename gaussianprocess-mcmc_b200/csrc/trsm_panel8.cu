@@ -44,7 +44,7 @@ __device__ __forceinline__ void dmma884_8(double &c0, double &c1, double a, doub
 }
 
 __global__ void __launch_bounds__(T8_THREADS, 2)
-trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW, int nblk)
+trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W, long long strideW, int nblk, int row_start, int n_mat)
 {
     extern __shared__ __align__(16) double sm[];
     double *Lb = sm;                              // 10 lower 32x32 blocks of L11
@@ -56,6 +56,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
     const int ld = A.ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
+    const int ncv = min(NB, n_mat - j0);          // columns of this block column that exist (ragged last block: < NB)
 
     for (int e = tid; e < T8_NLB * 32 * 16; e += T8_THREADS) {        // 16 16-byte pieces per block row
         const int blk = e / (32 * 16), rem = e - blk * 32 * 16;
@@ -63,8 +64,15 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
         int bi = 0;
         while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
         const int bj = blk - bi * (bi + 1) / 2;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&Lb[blk * T8_LBLK + r * T8_B + c2]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)(j0 + bi * 32 + r) * ld + j0 + bj * 32 + c2));
+        double *dstp = &Lb[blk * T8_LBLK + r * T8_B + c2];
+        const int gr = j0 + bi * 32 + r, gc = j0 + bj * 32 + c2;
+        if (gr < n_mat && gc < n_mat) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dstp);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)gr * ld + gc));
+        } else {                                  // beyond the matrix (ragged last block solved for border rows): identity
+            dstp[0] = (gr == gc) ? 1.0 : 0.0;
+            dstp[1] = (gr == gc + 1) ? 1.0 : 0.0;
+        }
     }
     const double *Wb = W + (size_t)m * strideW;
     for (int e = tid; e < T8_NB8 * 8 * 4; e += T8_THREADS) {          // 4 pieces per row of an 8x8 block
@@ -78,7 +86,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
     // kept the DMMA pipe at 75 % when every CTA took a single block).
     // n_rows counts a border row too; the last row block takes every row that is left (at most 64 + 1)
     const int rb_first = blockIdx.x;
-    const int row0_first = j0 + NB + rb_first * T8_ROWS;
+    const int row0_first = row_start + rb_first * T8_ROWS;
     const int rv_first = (rb_first == nblk - 1) ? min(T8_ROWS + 8, n_rows - row0_first) : T8_ROWS;
     // this warp's 8 rows as accumulator fragments: acc[b8] = row warp*8 + fr, cols b8*8 + 2fk, +1
     double acc[T8_NB8][2];
@@ -88,7 +96,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
 #pragma unroll
         for (int b8 = 0; b8 < T8_NB8; ++b8) {
             double2 v = make_double2(0.0, 0.0);
-            if (r_loc < rv_first) v = *reinterpret_cast<const double2 *>(grow0 + b8 * 8);
+            if (r_loc < rv_first && b8 * 8 + 2 * fk < ncv) v = *reinterpret_cast<const double2 *>(grow0 + b8 * 8);
             acc[b8][0] = v.x;
             acc[b8][1] = v.y;
         }
@@ -107,7 +115,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
     __syncthreads();
 
     for (int rb = rb_first; rb < nblk; rb += gridDim.x) {
-    const int row0 = j0 + NB + rb * T8_ROWS;
+    const int row0 = row_start + rb * T8_ROWS;
     const int rows_valid = (rb == nblk - 1) ? min(T8_ROWS + 8, n_rows - row0) : T8_ROWS;
     if (warp * 8 >= rows_valid) continue;         // nothing to solve (no border row, or a ragged last block)
     double *grow = Ab + (size_t)(row0 + min(r_loc, max(rows_valid, 1) - 1)) * ld + j0 + 2 * fk;
@@ -115,7 +123,7 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
 #pragma unroll
         for (int b8 = 0; b8 < T8_NB8; ++b8) {
             double2 v = make_double2(0.0, 0.0);
-            if (r_loc < rows_valid) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
+            if (r_loc < rows_valid && b8 * 8 + 2 * fk < ncv) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
             acc[b8][0] = v.x;
             acc[b8][1] = v.y;
         }
@@ -147,7 +155,11 @@ trsm_panel8_kernel(BatchView A, int n_rows, int j0, const double *__restrict__ W
             dmma884_8(acc[bp][0], acc[bp][1], nx1, lp.y);
         }
         // ---- the finished 8 columns leave from the accumulator registers (4 lanes x 16 bytes per row)
-        if (r_loc < rows_valid) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
+        if (r_loc < rows_valid) {
+            const int c = b8 * 8 + 2 * fk;
+            if (c + 1 < ncv) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
+            else if (c < ncv) grow[b8 * 8] = x0;
+        }
     }
     }
 }
@@ -265,9 +277,13 @@ int launch_inv_blocks8(BatchView A, int n, double *W, long long strideW, int B, 
 static int g_trsm_blocks_per_cta = 0;
 void set_trsm_blocks_per_cta(int v) { g_trsm_blocks_per_cta = v; }
 
-int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s)
+int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long long strideW, int B, cudaStream_t s, int row_start, int n_mat)
 {
-    int rows = n_rows - j0 - NB;
+    // default: every row below the diagonal block; row_start / n_mat: only the rows from row_start on (the border rows
+    // of the LAST block column, whose diagonal block may be ragged: L11 rows / columns >= n_mat read as identity)
+    if (row_start < 0) row_start = j0 + NB;
+    if (n_mat < 0) n_mat = 0x7fffffff;
+    int rows = n_rows - row_start;
     if (B <= 0 || rows <= 0) return 0;
     if ((A.ld & 1) || (j0 & 1)) { set_error("trsm_panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
     if (rows > 1 && rows % T8_ROWS == 1) rows -= 1;         // 64 k + 1: the extra row rides in the last CTA
@@ -285,7 +301,7 @@ int launch_trsm_panel8(BatchView A, int n_rows, int j0, const double *W, long lo
     }
     dim3 grid((nblk + per_cta - 1) / per_cta, B);
     prof_begin(KC_TRSM, s);
-    trsm_panel8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n_rows, j0, W, strideW, nblk);
+    trsm_panel8_kernel<<<grid, T8_THREADS, T8_SMEM, s>>>(A, n_rows, j0, W, strideW, nblk, row_start, n_mat);
     prof_end(KC_TRSM, s);
     GPMC_LAUNCH_CHECK();
     return 0;

@@ -97,13 +97,11 @@ class crossValid(Framework):
         return self.x[train_id, :], self.y[train_id, 0], self.x[test_id, :], self.y[test_id, 0], test_id
 
     def execute(self, updOpt='mcmcSml', iterMCMC=1000, out_dir='./output'):
-        import types
-        from .kcGP import covK, likK
+        from .kcGP import likK
         from .kcMCMC import sliceSample
         assert updOpt == 'mcmcSml', 'only the MCMC path is part of this package'
         originalX, originalY = self.x[:], self.y[:]
         results = {}
-        zero_mean = types.SimpleNamespace(getMean=lambda a: np.zeros((a.shape[0], 1)))
         for gap in self.gapArray:
             gapLLK = []
             for fold in range(gap + self.windowSize):
@@ -112,15 +110,19 @@ class crossValid(Framework):
                 self.x, self.y = trX, trY.reshape(-1, 1)
                 foldF, foldHyp = self.runSimulMCMC(iterMCMC)
                 upper, lower = 100. - np.mean(self.y), 0. - np.mean(self.y)
+                # every 10th sample of the last tenth of the chain (framework.py:223), predicted in ONE batched device pass
+                sel = list(range(iterMCMC * 9 // 10 - 1, iterMCMC, 10))
+                liks = {}
+
+                def lik_for(sn):
+                    liks[sn] = likK.TruncatedGauss2(upper=upper, lower=lower, log_sigma=np.log(sn))
+                    return liks[sn]
+                ys_all, _, _, fs2_all = sliceSample.inf_mcmc_batched(foldF[:, sel], foldHyp[:, sel].T, self.x, self.y, valX, lik_for)
                 foldLLK = []
-                for i in range(iterMCMC * 9 // 10 - 1, iterMCMC, 10):                  # framework.py:223
-                    ll, sf, sn = foldHyp[0, i], foldHyp[1, i], foldHyp[2, i]
-                    trunclik = likK.TruncatedGauss2(upper=upper, lower=lower, log_sigma=np.log(sn))
-                    model = types.SimpleNamespace(x=self.x, y=self.y, xs=valX, meanfunc=zero_mean,
-                                                  covfunc=covK.RBF(np.log(ll), np.log(sf)), likfunc=trunclik)
-                    ys, _, _, fs2 = sliceSample.inf_mcmc(foldF[:, i].reshape(-1, 1), model)
+                for k, i in enumerate(sel):
+                    trunclik = liks[foldHyp[2, i]]
                     trunclik.upper, trunclik.lower = 100., 0.                           # framework.py:241-242
-                    foldLLK.append(trunclik.evaluate(y=ys, mu=valY.reshape(-1, 1), s2=fs2) / ys.shape[0])
+                    foldLLK.append(trunclik.evaluate(y=ys_all[k], mu=valY.reshape(-1, 1), s2=fs2_all[k]) / ys_all[k].shape[0])
                 gapLLK.append(float(np.mean(foldLLK)))
             self.output(gap, foldHyp.T, foldF, gapLLK, out_dir=out_dir)                 # framework.py:248 (last fold's chain and data)
             self.x, self.y = originalX, originalY

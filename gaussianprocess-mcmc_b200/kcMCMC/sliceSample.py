@@ -92,57 +92,75 @@ def aux_var_model(f, K, sn, g=None):
 
 def elliptical_slice(f, x, y, hyp):
     """Elliptical slice sampling update of ``f`` -- same contract as ``sliceSample.py:15-74`` (dead code in the reference:
-    both call sites are commented out).  ``nu ~ N(0, K)`` is drawn as ``chol(K) z`` on the device; the reference draws it
-    through numpy's SVD route (``:41``), so the two agree in distribution, not sample by sample."""
-    from ..kcGP import covK, likK, tools
-    f = np.asarray(f, dtype=np.float64).reshape(-1)
+    both call sites are commented out).  The whole update runs on the device (``gpmc_ess_sweep``): ``nu = chol(K) z`` and
+    the bracket-shrinking loop on the ellipse.  The reference draws ``nu ~ N(0, K)`` through numpy's SVD route (``:41``),
+    so the two agree in distribution, not sample by sample; the global numpy stream is consumed like the reference does
+    (N normals, then one uniform for the slice level, one for the angle, one per rejected proposal)."""
+    import torch
+    f = np.array(f, dtype=np.float64).reshape(-1)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
-    nobs = f.shape[0]
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    hyp = np.asarray(hyp, dtype=np.float64).reshape(-1)
+    z = np.random.standard_normal(f.shape[0])
+    u = np.random.random_sample()
+    state = np.random.get_state()
+    th = np.random.random_sample(MAX_TRIPS)
+    F = torch.tensor(f[None]).cuda()
+    ntrips, status, info = ops.ess_sweep(x, y, F, hyp[None], tape=ops.EssTape([u], th[None], z=z[None]), max_trips=MAX_TRIPS)
+    np.random.set_state(state)
+    np.random.random_sample(int(ntrips.item()))          # the angle + one redraw per rejected proposal
+    st = int(status.item())
+    if st == 2:
+        raise np.linalg.LinAlgError('not positive definite, even with jitter.')
+    if st != 0:
+        raise RuntimeError('slice did not close within %d proposals' % MAX_TRIPS)
+    return F.cpu().numpy()[0]
+
+
+def inf_mcmc_batched(F, Hyp, x, y, xs, lik_factory, mean_x=None, mean_xs=None):
+    """``inf_mcmc`` (``sliceSample.py:234-284``) for S stored samples with their own hyper-parameters in ONE device pass
+    (``gpmc_predict_batched``) -- what the loops at ``framework.py:223-243`` / ``plotResult.py:98-121`` do one sample at a
+    time.  ``F[N, S]`` latent samples, ``Hyp[S, P]``; ``lik_factory(sn) -> likfunc`` builds the predictive likelihood of a
+    sample (``likK.TruncatedGauss2``); ``mean_x[N,1]`` / ``mean_xs[ns,1]`` are the mean function's values (zero when
+    omitted).  Returns arrays ``(ym[S, ns, 1], ys_lw[S, ns, 1], ys_up[S, ns, 1], Fs2[S, ns, 1])``."""
+    F = np.asarray(F, dtype=np.float64)
+    Hyp = np.atleast_2d(np.asarray(Hyp, dtype=np.float64))
+    y = np.asarray(y, dtype=np.float64)
     my = np.mean(y)
-    K = covK.RBF(np.log(hyp[0]), np.log(hyp[1])).getCovMatrix(x=x, mode='train')
-    nu = np.dot(tools.jitchol(K), np.random.standard_normal(nobs))
-    lik_func = likK.TruncatedGauss2(upper=100 - my, lower=0 - my, log_sigma=np.log(hyp[2]))
-    cur_llk = lik_func.evaluate(y=y - my, mu=f) + np.log(np.random.uniform())
-    theta = np.random.uniform(high=2. * np.pi)
-    theta_min, theta_max = theta - 2. * np.pi, theta
-    while True:
-        prop_f = f * np.cos(theta) + nu * np.sin(theta)
-        prop_llk = lik_func.evaluate(y=y - my, mu=prop_f)
-        if prop_llk > cur_llk and np.isfinite(prop_llk):
-            return prop_f
-        if theta >= 0:
-            theta_max = theta
-        else:
-            theta_min = theta
-        theta = np.random.uniform(low=theta_min, high=theta_max)
+    S, ns = Hyp.shape[0], np.asarray(xs).shape[0]
+    m = np.zeros((F.shape[0], 1)) if mean_x is None else np.asarray(mean_x, dtype=np.float64).reshape(-1, 1)
+    ms = np.zeros((ns, 1)) if mean_xs is None else np.asarray(mean_xs, dtype=np.float64).reshape(-1, 1)
+    fmu, fs2, info = ops.predict_batched(x, xs, np.ascontiguousarray((F - m).T), Hyp)
+    info = info.cpu().numpy()
+    if np.any(info != 0):
+        raise np.linalg.LinAlgError('not positive definite, even with jitter (sample %d)' % int(np.flatnonzero(info)[0]))
+    fmu, fs2 = fmu.cpu().numpy(), fs2.cpu().numpy()
+    out = [np.zeros((S, ns, 1)) for _ in range(4)]
+    for s in range(S):
+        Fmu = ms + fmu[s].reshape(ns, 1)                                       # :266
+        Fs2 = np.maximum(fs2[s].reshape(ns, 1), 0)                             # :273
+        Ymu, Lower, Upper = lik_factory(Hyp[s, -1]).evaluate(mu=Fmu, s2=Fs2)   # :279
+        out[0][s] = np.reshape(np.mean(Ymu, axis=1), (ns, 1)) + my
+        out[1][s] = np.reshape(np.mean(Lower, axis=1), (ns, 1)) + my
+        out[2][s] = np.reshape(np.mean(Upper, axis=1), (ns, 1)) + my
+        out[3][s] = Fs2
+    return tuple(out)
 
 
 def inf_mcmc(f, model, ys=0):
     """Predictive inference ``fs | f`` from stored MCMC samples -- same contract as ``sliceSample.py:234-284``
-    (``model`` has ``x, y, xs, meanfunc, covfunc, likfunc``); every O(N^3)/O(N^2) step goes through the GPU-backed
-    ``kcGP`` primitives (``jitchol``, ``solve_chol``, ``getCovMatrix``), the rest is the reference's own array glue."""
-    from ..kcGP import tools
-    x, y, xs = model.x, model.y, model.xs
-    my = np.mean(y)
-    n_samples = f.shape[1]
-    ns = xs.shape[0]
-    n, D = x.shape
-    m = np.tile(model.meanfunc.getMean(x), (1, n_samples))
-    K = model.covfunc.getCovMatrix(x=x, mode='train')
-    sn2 = model.likfunc.sn ** 2.
-    L = tools.jitchol(K / sn2 + np.eye(n)).T                        # upper
-    alpha = tools.solve_chol(L, f - m) / sn2
-    sW = np.ones((n, 1)) / np.sqrt(sn2)
-    kss = model.covfunc.getCovMatrix(z=xs, mode='self_test')
-    Ks = model.covfunc.getCovMatrix(x=x, z=xs, mode='cross')
-    ms = model.meanfunc.getMean(xs)
-    Fmu = np.tile(ms, (1, n_samples)) + np.dot(Ks.T, alpha)
-    V = ops.trsv_lower(np.ascontiguousarray(L.T), np.ascontiguousarray((np.tile(sW, (1, ns)) * Ks).T)).cpu().numpy().T
-    fs2 = kss - np.array([(V * V).sum(axis=0)]).T
-    Fs2 = np.maximum(fs2, 0)
-    Fmu = np.mean(Fmu, axis=1, keepdims=True)
-    Ymu, Lower, Upper = model.likfunc.evaluate(mu=Fmu, s2=Fs2)
-    ym = np.reshape(np.mean(Ymu, axis=1), (ns, 1)) + my
-    ys_lw = np.reshape(np.mean(Lower, axis=1), (ns, 1)) + my
-    ys_up = np.reshape(np.mean(Upper, axis=1), (ns, 1)) + my
-    return ym, ys_lw, ys_up, Fs2
+    (``model`` has ``x, y, xs, meanfunc, covfunc, likfunc``; ``f[N, n_samples]`` share the model's hyper-parameters).
+    The prediction is linear in ``f`` and the reference averages it over the samples (``:275``), so one right-hand side
+    -- the sample mean -- goes through the batched device path."""
+    f = np.asarray(f, dtype=np.float64)
+    if f.ndim == 1:
+        f = f.reshape(-1, 1)
+    cov_hyp = np.exp(np.asarray(model.covfunc.hyp, dtype=np.float64))          # (ell.., sf) natural scale
+    hyp = np.concatenate([cov_hyp, [model.likfunc.sn]])
+    fbar = np.mean(f, axis=1, keepdims=True)
+    likfunc = model.likfunc
+    ym, lw, up, Fs2 = inf_mcmc_batched(fbar, hyp[None], model.x, model.y, model.xs, lambda sn: likfunc,
+                                       mean_x=model.meanfunc.getMean(model.x), mean_xs=model.meanfunc.getMean(model.xs))
+    return ym[0], lw[0], up[0], Fs2[0]

@@ -250,6 +250,65 @@ def sds_sweep(x, y, F, Hyp, scale, it, my=None, tape=None, seed=0, chain0=0, max
     return ntrips, loglik, status
 
 
+def sds_run(x, y, F, Hyp, scale, it0, n_iters, my=None, seed=0, chain0=0, max_trips=64, prior_k=None, prior_theta=None,
+            jitter_policy=JITTER_PYGPS, workspace=None, chains_per_wave=None, keep_f_every=0):
+    """``n_iters`` surrogate-data slice-sampling transitions per chain in ONE call (``gpmc_sds_run``): the caller loop of
+    ``framework.py:68-75`` for every chain, each chain advancing on its own inside the resident device loop.
+
+    ``F[B,N]`` / ``Hyp[B,P]`` hold the state on entry and the final state on return.  Returns device tensors
+    ``(hist_hyp[B, n_iters, P], hist_loglik[B, n_iters], hist_trips[B, n_iters], hist_f[B, n_keep, N] or None, n_exhausted)``.
+    Results are those of ``n_iters`` calls of :func:`sds_sweep` with ``it = it0 .. it0 + n_iters - 1`` bit for bit."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    N, D = x.shape
+    if not (F.is_cuda and F.dtype == torch.float64 and F.is_contiguous() and F.dim() == 2 and F.shape[1] == N):
+        raise ValueError('F must be a contiguous CUDA float64 tensor [B, N]')
+    if not (Hyp.is_cuda and Hyp.dtype == torch.float64 and Hyp.is_contiguous() and Hyp.dim() == 2):
+        raise ValueError('Hyp must be a contiguous CUDA float64 tensor [B, P]')
+    B, P = Hyp.shape
+    kind = kind_of(D, P)
+    if my is None:
+        my = float(np.mean(np.asarray(y.cpu() if hasattr(y, 'cpu') else y, dtype=np.float64)))
+    y = _f64_cuda(torch, y, 'y').reshape(-1)
+    k, th = prior_constants(P - 2)
+    k = _f64_cuda(torch, k if prior_k is None else prior_k, 'prior_k')
+    th = _f64_cuda(torch, th if prior_theta is None else prior_theta, 'prior_theta')
+    scale = _f64_cuda(torch, scale, 'scale').reshape(-1)
+    n_iters = int(n_iters)
+    hist_hyp = torch.zeros((B, n_iters, P), dtype=torch.float64, device='cuda')
+    hist_ll = torch.zeros((B, n_iters), dtype=torch.float64, device='cuda')
+    hist_trips = torch.zeros((B, n_iters), dtype=torch.int32, device='cuda')
+    n_keep = (n_iters + keep_f_every - 1) // keep_f_every if keep_f_every else 0
+    hist_f = torch.zeros((B, n_keep, N), dtype=torch.float64, device='cuda') if n_keep else None
+    n_exh = torch.zeros((1,), dtype=torch.int32, device='cuda')
+    if B == 0 or n_iters == 0:
+        return hist_hyp, hist_ll, hist_trips, hist_f, 0
+    wsobj = workspace or _default_ws
+    have = 0 if wsobj.buf is None else wsobj.buf.numel()
+    explicit_wave = chains_per_wave is not None
+    if chains_per_wave is None:
+        chains_per_wave = B
+        if lib.gpmc_sds_workspace_bytes(N, P, B) > have:
+            free, _ = torch.cuda.mem_get_info()
+            budget = (free + have) * 6 // 10
+            while chains_per_wave > 1 and lib.gpmc_sds_workspace_bytes(N, P, chains_per_wave) > max(budget, have):
+                chains_per_wave = (chains_per_wave + 1) // 2
+    need = lib.gpmc_sds_workspace_bytes(N, P, min(B, chains_per_wave))
+    ws = wsobj.get(torch, need)
+    ws_bytes = need if explicit_wave else ws.numel()
+    rc = lib.gpmc_sds_run(x.data_ptr(), y.data_ptr(), N, D, F.data_ptr(), Hyp.data_ptr(), B, P, kind,
+                          scale.data_ptr(), k.data_ptr(), th.data_ptr(), int(it0), n_iters, my, 0.0 - my, 100.0 - my,
+                          int(seed), int(chain0), int(max_trips), jitter_policy,
+                          hist_hyp.data_ptr(), hist_ll.data_ptr(), hist_trips.data_ptr(),
+                          None if hist_f is None else hist_f.data_ptr(), int(keep_f_every), int(n_keep),
+                          n_exh.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_sds_run')
+    return hist_hyp, hist_ll, hist_trips, hist_f, int(n_exh.item())
+
+
 def _pad_matrix(torch, A, ld):
     """Copy a host/device [N, N] matrix into a zero-padded CUDA [N, ld] buffer."""
     A = _f64_cuda(torch, A, 'A')
@@ -338,6 +397,102 @@ def tg2_loglik(y, mu, sn, lower, upper, my=0.0):
                              out.data_ptr(), _stream_ptr(torch))
     _lib.check(rc, 'gpmc_tg2_loglik')
     return out
+
+
+def predict_batched(x, xs, fm, hyp, jitter_policy=JITTER_PYGPS, workspace=None):
+    """``inf_mcmc``'s linear algebra (``sliceSample.py:256-270``) for S stored samples at once.
+
+    ``fm[S, N]`` = ``f_s - m`` (centred latent samples), ``hyp[S, P]`` their hyper-parameters, ``xs[M, D]`` test inputs.
+    Returns device tensors ``(fmu[S, M], fs2[S, M], info[S])`` with ``fmu = Ks^T alpha`` (add ``ms`` yourself) and
+    ``fs2 = kss - sum V^2`` (unclamped)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    xs = _f64_cuda(torch, xs, 'xs')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    if xs.dim() == 1:
+        xs = xs.reshape(-1, 1)
+    fm = _f64_cuda(torch, fm, 'fm')
+    hyp = _f64_cuda(torch, hyp, 'hyp')
+    if fm.dim() == 1:
+        fm = fm.reshape(1, -1)
+    if hyp.dim() == 1:
+        hyp = hyp.reshape(1, -1)
+    N, D = x.shape
+    M = xs.shape[0]
+    S, P = hyp.shape
+    if fm.shape != (S, N) or xs.shape[1] != D:
+        raise ValueError('fm must be [S=%d, N=%d] and xs [M, D=%d]' % (S, N, D))
+    fmu = torch.empty((S, M), dtype=torch.float64, device='cuda')
+    fs2 = torch.empty((S, M), dtype=torch.float64, device='cuda')
+    info = torch.zeros((S,), dtype=torch.int32, device='cuda')
+    if S == 0 or M == 0:
+        return fmu, fs2, info
+    ws = (workspace or _default_ws).get(torch, lib.gpmc_predict_workspace_bytes(N, M, S))
+    rc = lib.gpmc_predict_batched(x.data_ptr(), N, D, xs.data_ptr(), M, fm.data_ptr(), hyp.data_ptr(), S, P, kind_of(D, P),
+                                  jitter_policy, fmu.data_ptr(), fs2.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_predict_batched')
+    return fmu, fs2, info
+
+
+class EssTape(object):
+    """Explicit randomness of one elliptical-slice update for B chains in the reference's draw order
+    (``sliceSample.py:41,51,54,74``): ``nu[B,N]`` (the N(0,K) draw itself) or ``z[B,N]`` (nu = chol(K) z),
+    ``u[B]`` (slice level), ``theta[B,T]`` (initial angle, then one redraw per rejected proposal), all U(0,1)/N(0,1)."""
+
+    def __init__(self, u, theta, nu=None, z=None):
+        self.u = np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64)
+        self.theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        self.nu = None if nu is None else np.ascontiguousarray(np.atleast_2d(nu), dtype=np.float64)
+        self.z = None if z is None else np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+
+
+def ess_sweep(x, y, F, Hyp, it=0, my=None, tape=None, seed=0, chain0=0, max_trips=256, jitter_policy=JITTER_PYGPS, workspace=None):
+    """One elliptical-slice update of ``F[B,N]`` in place (``sliceSample.py:15-74``) for B chains with ``Hyp[B,P]``.
+    Returns ``(ntrips[B], status[B], info[B])`` device tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    x = _f64_cuda(torch, x, 'x')
+    if x.dim() == 1:
+        x = x.reshape(-1, 1)
+    N, D = x.shape
+    if not (F.is_cuda and F.dtype == torch.float64 and F.is_contiguous() and F.dim() == 2 and F.shape[1] == N):
+        raise ValueError('F must be a contiguous CUDA float64 tensor [B, N]')
+    Hyp = _f64_cuda(torch, Hyp, 'Hyp')
+    if Hyp.dim() == 1:
+        Hyp = Hyp.reshape(1, -1)
+    B, P = Hyp.shape
+    if F.shape[0] != B:
+        raise ValueError('F and Hyp disagree on the number of chains')
+    if my is None:
+        my = float(np.mean(np.asarray(y.cpu() if hasattr(y, 'cpu') else y, dtype=np.float64)))
+    y = _f64_cuda(torch, y, 'y').reshape(-1)
+    ntrips = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    status = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    info = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    if B == 0:
+        return ntrips, status, info
+    t_nu = t_z = t_u = t_th = None
+    ttrips = 0
+    if tape is not None:
+        if tape.u.shape != (B,) or tape.theta.shape[0] != B:
+            raise ValueError('tape shapes do not match B=%d' % B)
+        t_u, t_th = torch.tensor(tape.u).cuda(), torch.tensor(tape.theta).cuda()
+        ttrips = tape.theta.shape[1]
+        if tape.nu is not None:
+            t_nu = torch.tensor(tape.nu).cuda()
+        if tape.z is not None:
+            t_z = torch.tensor(tape.z).cuda()
+    ws = (workspace or _default_ws).get(torch, lib.gpmc_ess_workspace_bytes(N, B))
+    ptr = lambda t: None if t is None else t.data_ptr()
+    rc = lib.gpmc_ess_sweep(x.data_ptr(), y.data_ptr(), N, D, F.data_ptr(), Hyp.data_ptr(), B, P, kind_of(D, P),
+                            my, 0.0 - my, 100.0 - my, int(seed), int(chain0), int(it),
+                            ptr(t_nu), ptr(t_z), ptr(t_u), ptr(t_th), ttrips, int(max_trips), jitter_policy,
+                            ntrips.data_ptr(), status.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch))
+    _lib.check(rc, 'gpmc_ess_sweep')
+    return ntrips, status, info
 
 
 def set_tuning(key, value):

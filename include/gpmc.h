@@ -50,6 +50,7 @@ extern "C" {
 /* flags of gpmc_cov_assemble */
 #define GPMC_ASM_ADD_S      1   /* add S_ii (sliceSample.py:184-190) on the diagonal */
 #define GPMC_ASM_LOWER_ONLY 2   /* write only tiles on/below the diagonal (internal fast path) */
+#define GPMC_ASM_PRED       4   /* K / sn^2 + I, the matrix inf_mcmc factors (sliceSample.py:256-257) */
 
 /* jitter policies of the Cholesky (kcGP.tools.jitchol semantics) */
 #define GPMC_JITTER_NONE    0   /* one dpotrf attempt, asynchronous, info as LAPACK */
@@ -146,6 +147,23 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
                    void *ws_dev, size_t ws_bytes, void *stream);
 
 /*
+ * The caller loop of framework.py:68-75 / demoRegression.py:23-30 -- `for i in range(iters): propF, propHyp =
+ * surrogate_slice_sampling(propF, x, y, propHyp, scale, iter=i)` -- for B chains in ONE call: every chain runs its
+ * transitions iter_begin .. iter_begin + n_iters - 1 back to back inside the resident loop of gpmc_sds_sweep, so no chain
+ * waits for the slowest one at an iteration boundary (the workspace slots stay full until the call runs out of work).
+ * Randomness: Philox keyed by (seed, chain0 + chain, iteration) -- the results are those of n_iters gpmc_sds_sweep calls
+ * bit for bit.  F_dev / hyp_dev: state in, final state out.  History (any pointer may be NULL):
+ *   hist_hyp_dev[B, n_iters, P], hist_loglik_dev[B, n_iters] (log N(g; 0, K+S) at the sample), hist_trips_dev[B, n_iters],
+ *   hist_f_dev[B, n_keep, N]: f after iterations iter_begin + k * thin, k < n_keep;
+ *   n_exhausted_dev[1]: transitions that used up max_trips (their chain kept its state for that iteration).
+ */
+int gpmc_sds_run(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, double *hyp_dev, int B, int P,
+                 int kind, const double *scale_dev, const double *prior_k_dev, const double *prior_theta_dev, int iter_begin,
+                 int n_iters, double my, double lower, double upper, unsigned long long seed, unsigned chain0, int max_trips,
+                 int jitter_policy, double *hist_hyp_dev, double *hist_loglik_dev, int *hist_trips_dev, double *hist_f_dev,
+                 int thin, int n_keep, int *n_exhausted_dev, void *ws_dev, size_t ws_bytes, void *stream);
+
+/*
  * aux_var_model(f, K, sn, g) for one caller-supplied K (sliceSample.py:165-207).  K_dev[N][ld] (ld % 16 == 0, pad
  * columns zero), S_dev[ld] = diag of S (sliceSample.py:184-190; entries beyond N zero), g_dev[ld].  Outputs
  * L_dev = chol(K+S) (:196), m_dev[ld] = R S^-1 g (:204), C_dev = chol(R + 1e-11 I) (:205), both N x ld lower with
@@ -177,6 +195,36 @@ int gpmc_cov_cross(const double *x_dev, int N, const double *z_dev, int M, int D
  */
 int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ldmu, int N, int B, const double *sn_dev,
                     double lower, double upper, double *out_dev, void *stream);
+
+/*
+ * inf_mcmc (kcMCMC/sliceSample.py:234-284; callers framework.py:223-243, plotResult.py:121) for S stored MCMC samples at
+ * once.  Per sample s with hyper-parameters hyp[s] and centred latent vector fm[s] = f_s - m (the mean function is the
+ * caller's): factor K/sn^2 + I (:256-257, jitchol), and return
+ *     fmu[s][j] = (Ks^T alpha)_j,  alpha = (K + sn^2 I)^-1 fm        (:258,266; the caller adds ms)
+ *     fs2[s][j] = kss_j - sum_i V_ij^2,  V = L^-1 (sW o Ks)          (:262-263,269-270; the caller clamps at 0)
+ * for the M test inputs xs[M,D].  The 1 + M right-hand sides ride through the factorisation as border rows.
+ * info[s] as in gpmc_potrf_batched; a failed sample gets NaN.
+ */
+size_t gpmc_predict_workspace_bytes(int N, int M, int S);
+int gpmc_predict_batched(const double *x_dev, int N, int D, const double *xs_dev, int M, const double *fm_dev,
+                         const double *hyp_dev, int S, int P, int kind, int jitter_policy, double *fmu_dev, double *fs2_dev,
+                         int *info_dev, void *ws_dev, size_t ws_bytes, void *stream);
+
+/*
+ * elliptical_slice (kcMCMC/sliceSample.py:15-74) for B chains: F_dev[B,N] in/out, hyp_dev[B,P] (ell.., sf, sn).
+ *   nu ~ N(0, K): tape_nu[B,N] given -> used as is; else nu = chol(K) z with K = covK.RBF(...).getCovMatrix(x) (:38-39),
+ *                 z = tape_z[B,N] or Philox (the reference draws through numpy's SVD route, :41: equal in distribution)
+ *   tape_u[B]            U(0,1) for the slice level (:51);  tape_theta[B,tape_trips] U(0,1): the initial angle (:54) and
+ *                        one redraw per rejected proposal (:74); NULL -> Philox keyed by (seed, chain0 + chain, iter)
+ *   ntrips[B] proposals evaluated; status[B]: 0 accepted, 1 max_trips used up (state kept), 2 chol(K) failed even with
+ *   jitter (the reference raises LinAlgError); info[B] = status of the factorisation.
+ */
+size_t gpmc_ess_workspace_bytes(int N, int B);
+int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, double *F_dev, const double *hyp_dev, int B, int P,
+                   int kind, double my, double lower, double upper, unsigned long long seed, unsigned chain0, int iter,
+                   const double *tape_nu, const double *tape_z, const double *tape_u, const double *tape_theta, int tape_trips,
+                   int max_trips, int jitter_policy, int *ntrips_dev, int *status_dev, int *info_dev,
+                   void *ws_dev, size_t ws_bytes, void *stream);
 
 /* Kernel tuning knobs for experiments.
  * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default).

@@ -155,6 +155,47 @@ def infmcmc_case(n=64, ns=17, n_samples=5, seed=808):
     return dict(x=x, y=y, xs=xs, hyp=hyp, f=f, ref_ym=ym, ref_lw=lw, ref_up=up, ref_Fs2=Fs2)
 
 
+def infmcmc_batched_case(n=96, ns=13, S=6, seed=909):
+    """The reference's ``inf_mcmc`` called once per stored sample, each with its own (ll, sf, sn) -- the loop of
+    ``framework.py:223-243`` -- as the fixture for the batched device path."""
+    import types
+    x, y = _series(n)
+    rs = np.random.RandomState(seed)
+    xs = np.sort(rs.uniform(0, n, size=(ns, 1)), axis=0)
+    Hyp = np.column_stack([rs.uniform(1.5, 7., S), rs.uniform(2., 9., S), rs.uniform(0.6, 2.8, S)])
+    F = (y - y.mean())[:, None] * rs.uniform(0.4, 0.9, S)[None, :] + 0.3 * rs.standard_normal((n, S))
+    mod = rl.load_literal(fresh=True)
+    out = [[], [], [], []]
+    for s in range(S):
+        model = types.SimpleNamespace(x=x, y=y.reshape(-1, 1), xs=xs, meanfunc=_ZeroMean(),
+                                      covfunc=kcgp_shim.RBF(np.log(Hyp[s, 0]), np.log(Hyp[s, 1])),
+                                      likfunc=kcgp_shim.TruncatedGauss2(upper=100 - y.mean(), lower=0 - y.mean(), log_sigma=np.log(Hyp[s, 2])))
+        res = mod.inf_mcmc(F[:, s:s + 1], model)
+        uni = so.inf_mcmc_unit(F[:, s], x, y, xs, Hyp[s])
+        for k in range(4):
+            assert np.array_equal(res[k], uni[k]), 'restated inf_mcmc differs from the literal one'
+            out[k].append(res[k])
+    return dict(x=x, y=y, xs=xs, Hyp=Hyp, F=F, ref_ym=np.stack(out[0]), ref_lw=np.stack(out[1]), ref_up=np.stack(out[2]),
+                ref_Fs2=np.stack(out[3]))
+
+
+def ess_case(n, seed, hyp, f_scale):
+    """The reference's ``elliptical_slice`` (``sliceSample.py:15-74``) run UNMODIFIED on a tape; ``nu`` is the Cholesky
+    draw ``jitchol(K) z`` (``z`` is stored too, so the device's own draw can be checked against it)."""
+    x, y = _series(n)
+    rs = np.random.RandomState(seed)
+    hyp = np.asarray(hyp, dtype=np.float64)
+    f = f_scale * (y - y.mean()) + 0.2 * rs.standard_normal(n)
+    z = rs.standard_normal(n)
+    nu = so.ess_nu_from_z(x, hyp, z)
+    tape = rl.EssTape(nu, rs.random_sample(), rs.random_sample(64))
+    pf, trips = rl.run_literal_ess_with_tape(f, x, y, hyp, tape)
+    of, otrips = so.elliptical_slice(f, x, y, hyp, tape)
+    assert np.array_equal(pf, of) and trips == otrips, 'restated elliptical_slice differs from the literal one'
+    cond_K = float(np.linalg.cond(so.cov_matrix(x, np.concatenate([hyp[:-1], [1.0]]))))
+    return dict(x=x, y=y, hyp=hyp, f=f, z=z, nu=nu, u=tape.u, theta=tape.theta, ref_prop_f=pf, ref_trips=trips, cond_K=cond_K)
+
+
 def main():
     if not rl.available():
         sys.exit('reference tree not present: fixtures can only be generated in the build container')
@@ -180,6 +221,13 @@ def main():
     print('loglik_ard: %d cases' % len(rows))
     np.savez_compressed(os.path.join(GOLDEN, 'infmcmc_N64.npz'), **infmcmc_case())
     print('infmcmc_N64 written')
+    np.savez_compressed(os.path.join(GOLDEN, 'infmcmc_batched_N96.npz'), **infmcmc_batched_case())
+    print('infmcmc_batched_N96 written')
+    for n, seed, hyp, fs in ((64, 61, [3., 5., 1.5], 0.8), (200, 62, [5., 4., 2.5], 0.6), (200, 63, [1., 10., 1.2], 0.0), (455, 64, [8., 3., 2.0], 0.9),
+                             (200, 65, [0.35, 2.0, 0.2], 0.7)):
+        out = ess_case(n, seed, hyp, fs)
+        np.savez_compressed(os.path.join(GOLDEN, 'ess_N%d_s%d.npz' % (n, seed)), **out)
+        print('ess_N%d_s%d: %d proposals' % (n, seed, out['ref_trips']))
     ch = chain_case()
     np.savez_compressed(os.path.join(GOLDEN, 'chain_N64.npz'), **ch)
     print('chain_N64: trips mean %.2f max %d; final hyp %s' % (ch['ref_trips'].mean(), ch['ref_trips'].max(), ch['ref_histHyp'][:, -1]))

@@ -117,3 +117,43 @@ def run_literal_with_tape(f, x, y, hyp, scale, it, tape):
                                                     np.asarray(y, dtype=np.float64), np.array(hyp, dtype=np.float64),
                                                     np.asarray(scale, dtype=np.float64), iter=it)
     return np.asarray(prop_f), np.asarray(prop_hyp), rnd.trips
+
+
+class EssTape(object):
+    """Explicit randomness for ONE ``elliptical_slice`` call in the reference's draw order (``sliceSample.py``):
+    ``nu[N]`` the ``N(0, K)`` draw of ``:41``, ``u`` U(0,1) for the slice level (``:51``), ``theta[T]`` U(0,1): the initial
+    angle (``:54``) and one redraw per rejected proposal (``:74``)."""
+
+    def __init__(self, nu, u, theta):
+        self.nu = np.asarray(nu, dtype=np.float64)
+        self.u = float(u)
+        self.theta = np.asarray(theta, dtype=np.float64)
+
+
+class _EssTapeRandom(object):
+    def __init__(self, tape):
+        self.tape = tape
+        self.calls = 0          # uniform() calls: 0 -> u, 1 -> theta[0], k -> theta[k-1]
+
+    def multivariate_normal(self, mean, cov, size):
+        return (np.asarray(mean) + self.tape.nu).reshape(1, -1)            # :41 (mean is zero)
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        if self.calls == 0:
+            u = self.tape.u
+        else:
+            if self.calls - 1 >= self.tape.theta.shape[0]:
+                raise RuntimeError('tape exhausted after %d angles' % (self.calls - 1))
+            u = self.tape.theta[self.calls - 1]
+        self.calls += 1
+        return float(low + (high - low) * u)
+
+
+def run_literal_ess_with_tape(f, x, y, hyp, tape):
+    """Run the UNMODIFIED ``elliptical_slice`` (``sliceSample.py:15-74``) on a tape.  Returns ``(prop_f, n_proposals)``."""
+    mod = load_literal(fresh=True)
+    rnd = _EssTapeRandom(tape)
+    mod.np = _NumpyProxy(rnd)
+    prop_f = mod.elliptical_slice(np.array(f, dtype=np.float64), np.asarray(x, dtype=np.float64),
+                                  np.asarray(y, dtype=np.float64), np.array(hyp, dtype=np.float64))
+    return np.asarray(prop_f), rnd.calls - 1

@@ -273,3 +273,80 @@ def run_chain(x, y, hyp0, scale, iters, seed, f0=None, start_iter=0, max_trips=6
         histHyp[:, i] = propHyp
         trips[i] = tr.n_trips
     return histF, histHyp, trips
+
+
+# ------------------------------------------------------------ f4: elliptical slice sampling
+def elliptical_slice(f, x, y, hyp, tape, max_trips=None):
+    """``elliptical_slice`` (``sliceSample.py:15-74``) on a tape (``reference_loader.EssTape``: ``nu``, ``u``, ``theta[T]``).
+    Returns ``(prop_f, n_proposals)``."""
+    f = np.asarray(f, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    hyp = np.asarray(hyp, dtype=np.float64)
+    my = np.mean(y)                                                          # :36
+    nu = np.asarray(tape.nu, dtype=np.float64)                               # :38-43 (the N(0, K) draw is on the tape)
+    upper = 100 - my                                                         # :45
+    lower = 0 - my                                                           # :46
+    sn = np.exp(np.log(hyp[-1]))                                             # :47 log_sigma round trip
+    cur_llk = trunc_gauss2_loglik(y - my, f, sn, lower, upper)               # :50
+    cur_llk = cur_llk + np.log(tape.u)                                       # :51
+    theta = 0. + (2. * np.pi - 0.) * tape.theta[0]                           # :54
+    theta_min = theta - 2. * np.pi                                           # :55
+    theta_max = theta                                                        # :56
+    trip = 0
+    while True:                                                              # :59
+        trip += 1
+        prop_f = f * np.cos(theta) + nu * np.sin(theta)                      # :60
+        prop_llk = trunc_gauss2_loglik(y - my, prop_f, sn, lower, upper)     # :62
+        if prop_llk > cur_llk and np.isfinite(prop_llk):                     # :64
+            return prop_f, trip                                              # :66
+        if theta >= 0:
+            theta_max = theta                                                # :69-70
+        else:
+            theta_min = theta                                                # :71-72
+        if trip >= tape.theta.shape[0] or (max_trips is not None and trip >= max_trips):
+            raise RuntimeError('tape exhausted after %d proposals' % trip)
+        theta = theta_min + (theta_max - theta_min) * tape.theta[trip]       # :74
+
+
+def ess_nu_from_z(x, hyp, z):
+    """``nu = jitchol(K) z`` with ``K = covK.RBF(log ll, log sf).getCovMatrix(x, 'train')`` (``:38-39``): the Cholesky
+    form of the ``N(0, K)`` draw the CUDA path uses (the reference's ``:41`` goes through numpy's SVD: same law)."""
+    K = cov_matrix(x, np.concatenate([np.asarray(hyp, dtype=np.float64)[:-1], [1.0]]))
+    return np.dot(kcgp_shim.jitchol(K), np.asarray(z, dtype=np.float64))
+
+
+# ------------------------------------------------------------ f2: predictive inference
+def inf_mcmc_unit(f, x, y, xs, hyp, lower=None, upper=None):
+    """``inf_mcmc`` (``sliceSample.py:234-284``) for ONE stored sample ``f[N]`` with hyper-parameters ``hyp`` and a zero
+    mean function, restated line by line.  Returns ``(ym, ys_lw, ys_up, Fs2, Fmu)`` (``Fmu`` before the likelihood)."""
+    x = np.asarray(x, dtype=np.float64)
+    xs = np.asarray(xs, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    hyp = np.asarray(hyp, dtype=np.float64)
+    n_ell = hyp.shape[0] - 2
+    my = np.mean(y)                                                          # :249
+    n = x.shape[0]
+    ns = xs.shape[0]
+    f = np.asarray(f, dtype=np.float64).reshape(n, 1)
+    if n_ell == 1:
+        cov = kcgp_shim.RBF(np.log(hyp[0]), np.log(hyp[1]))
+    else:
+        cov = kcgp_shim.RBFard(log_ell_list=list(np.log(hyp[:n_ell])), log_sigma=np.log(hyp[n_ell]))
+    lik = kcgp_shim.TruncatedGauss2(upper=(100 - my) if upper is None else upper, lower=(0 - my) if lower is None else lower,
+                                    log_sigma=np.log(hyp[-1]))
+    m = np.zeros((n, 1))                                                     # :254 (zero mean)
+    K = cov.getCovMatrix(x=x, mode='train')                                  # :255
+    sn2 = lik.sn ** 2.                                                       # :256
+    L = kcgp_shim.jitchol(K / sn2 + np.eye(n)).T                             # :257
+    alpha = kcgp_shim.solve_chol(L, f - m) / sn2                             # :258
+    sW = np.ones((n, 1)) / np.sqrt(sn2)                                      # :259
+    kss = cov.getCovMatrix(z=xs, mode='self_test')                           # :262
+    Ks = cov.getCovMatrix(x=x, z=xs, mode='cross')                           # :263
+    Fmu = np.zeros((ns, 1)) + np.dot(Ks.T, alpha)                            # :265-266
+    V = np.linalg.solve(L.T, np.tile(sW, (1, ns)) * Ks)                      # :269
+    fs2 = kss - np.array([(V * V).sum(axis=0)]).T                            # :270
+    Fs2 = np.maximum(fs2, 0)                                                 # :275
+    Fmu = np.mean(Fmu, axis=1, keepdims=True)                                # :277
+    Ymu, Lower, Upper = lik.evaluate(mu=Fmu, s2=Fs2)                         # :279
+    return (np.reshape(np.mean(Ymu, axis=1), (ns, 1)) + my, np.reshape(np.mean(Lower, axis=1), (ns, 1)) + my,
+            np.reshape(np.mean(Upper, axis=1), (ns, 1)) + my, Fs2, Fmu)

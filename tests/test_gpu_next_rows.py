@@ -1,5 +1,6 @@
 """SURVEY 8f "next" rows and the kcGP seam (8b): GPU-backed stand-ins for covK / tools / likK, the stand-alone
 aux_var_model, inf_mcmc, elliptical_slice and the Framework caller loop.  B200 only."""
+import glob
 import os
 import types
 
@@ -105,16 +106,119 @@ def test_inf_mcmc_matches_reference_fixture(gp):
     np.testing.assert_allclose(Fs2, z['ref_Fs2'], rtol=1e-8, atol=1e-12)
 
 
+def test_inf_mcmc_batched_matches_reference_fixture(gp):
+    """S stored samples, each with its own (ll, sf, sn), predicted in ONE device pass (gpmc_predict_batched: right-hand
+    sides carried through the factorisation as border rows) against the reference's inf_mcmc called once per sample."""
+    z = np.load(os.path.join(GOLDEN, 'infmcmc_batched_N96.npz'))
+    x, y, xs, Hyp, F = z['x'], z['y'], z['xs'], z['Hyp'], z['F']
+    lik = lambda sn: gp.kcGP.likK.TruncatedGauss2(upper=100 - y.mean(), lower=0 - y.mean(), log_sigma=np.log(sn))
+    ym, lw, up, Fs2 = gp.kcMCMC.sliceSample.inf_mcmc_batched(F, Hyp, x, y, xs, lik)
+    np.testing.assert_allclose(ym, z['ref_ym'], rtol=1e-9)
+    np.testing.assert_allclose(lw, z['ref_lw'], rtol=1e-8)
+    np.testing.assert_allclose(up, z['ref_up'], rtol=1e-8)
+    np.testing.assert_allclose(Fs2, z['ref_Fs2'], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize('n,ns,S', [(130, 3, 2), (257, 70, 5), (640, 33, 9), (1000, 200, 3)])
+def test_predict_batched_vs_oracle(gp, n, ns, S):
+    """Sizes around the panel width and with more right-hand sides than one CTA of the panel solve takes (ns > 64): the
+    border rows land in every position of the last row tile; compared with the oracle's restatement of :246-277."""
+    from oracle import sds_oracle as so
+    rs = np.random.RandomState(n + ns)
+    x, y = gp.synthetic.ih45_series(n)
+    xs = np.sort(rs.uniform(0, n, size=(ns, 1)), axis=0)
+    Hyp = np.column_stack([rs.uniform(1.5, 7., S), rs.uniform(2., 9., S), rs.uniform(0.6, 2.8, S)])
+    F = (y - y.mean())[:, None] * 0.7 + 0.3 * rs.standard_normal((n, S))
+    fmu, fs2, info = gp.ops.predict_batched(x, xs, np.ascontiguousarray(F.T), Hyp)
+    assert np.all(info.cpu().numpy() == 0)
+    fmu, fs2 = fmu.cpu().numpy(), fs2.cpu().numpy()
+    for s in range(S):
+        _, _, _, Fs2, Fmu = so.inf_mcmc_unit(F[:, s], x, y, xs, Hyp[s])
+        np.testing.assert_allclose(fmu[s], Fmu[:, 0], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(np.maximum(fs2[s], 0), Fs2[:, 0], rtol=1e-8, atol=1e-10)
+
+
+ESS = sorted(glob.glob(os.path.join(GOLDEN, 'ess_N*.npz')))
+
+
+@pytest.mark.parametrize('path', ESS, ids=[os.path.basename(p) for p in ESS])
+def test_elliptical_slice_matches_reference(gp, path):
+    """The device loop (gpmc_ess_sweep) on the tape the reference's own elliptical_slice (sliceSample.py:15-74) was run
+    on: the number of proposals is exact and f' matches to rounding; then the device's own Cholesky draw nu = chol(K) z
+    from the same z (the accept decisions are still the reference's)."""
+    import torch
+    from gpmc_b200 import ops
+    z = np.load(path)
+    assert len(ESS) >= 5
+    for mode in ('nu', 'z'):
+        F = torch.tensor(z['f'][None].copy()).cuda()
+        tape = ops.EssTape([float(z['u'])], z['theta'][None], nu=z['nu'][None] if mode == 'nu' else None,
+                           z=z['z'][None] if mode == 'z' else None)
+        nt, st, info = ops.ess_sweep(z['x'], z['y'], F, z['hyp'][None], tape=tape, max_trips=64)
+        assert int(st.item()) == 0 and int(info.item()) == 0
+        if mode == 'nu' or float(z['cond_K']) < 1e8:
+            assert int(nt.item()) == int(z['ref_trips']), (mode, int(nt.item()), int(z['ref_trips']))
+        # nu on the tape: f' = f cos(theta) + nu sin(theta) to rounding.  nu = chol(K) z on the device: K has no noise
+        # term; where it is well conditioned (short length-scale fixture) the draw matches the oracle's jitchol(K) z to
+        # 1e-9.  Where K is numerically singular (cond > 1e12: every smooth-kernel fixture) whether the first, jitter-free
+        # dpotrf attempt survives is decided by rounding, so two correct jitchol implementations may stop at different
+        # rungs of the ladder (jitter 0 vs 1e-6 mean(diag)): nu then agrees to ~1e-3 relative only -- stated bound 5e-3.
+        tol = 1e-12 if mode == 'nu' else (1e-9 if float(z['cond_K']) < 1e8 else 5e-3)
+        err = np.abs(F.cpu().numpy()[0] - z['ref_prop_f']).max()
+        assert err <= tol * max(1.0, np.abs(z['ref_prop_f']).max()), (mode, err, float(z['cond_K']))
+
+
+def test_elliptical_slice_batch_and_budget(gp):
+    """A batch of chains (different tapes, different trip counts) equals its chains run one by one; a chain that uses up
+    its budget keeps its state (status 1); Philox-driven updates are deterministic and keyed by the global chain id."""
+    import torch
+    from gpmc_b200 import ops
+    zs = [np.load(p) for p in ESS if '_N200_' in p]
+    x, y = zs[0]['x'], zs[0]['y']
+    F = torch.tensor(np.stack([z['f'] for z in zs])).cuda()
+    H = np.stack([z['hyp'] for z in zs])
+    tape = ops.EssTape([float(z['u']) for z in zs], np.stack([z['theta'] for z in zs]), nu=np.stack([z['nu'] for z in zs]))
+    nt, st, _ = ops.ess_sweep(x, y, F, H, tape=tape, max_trips=64)
+    for b, z in enumerate(zs):
+        assert int(nt[b].item()) == int(z['ref_trips']) and int(st[b].item()) == 0
+        np.testing.assert_allclose(F.cpu().numpy()[b], z['ref_prop_f'], rtol=1e-12, atol=1e-12)
+    z = zs[0]
+    F1 = torch.tensor(z['f'][None].copy()).cuda()
+    nt, st, _ = ops.ess_sweep(x, y, F1, z['hyp'][None], tape=ops.EssTape([float(z['u'])], z['theta'][None], nu=z['nu'][None]), max_trips=2)
+    assert int(st.item()) == 1 and int(nt.item()) == 2 and np.array_equal(F1.cpu().numpy()[0], z['f'])
+    F0 = np.stack([z['f'] for z in zs] * 3)
+    H0 = np.stack([z['hyp'] for z in zs] * 3)
+    Fa = torch.tensor(F0.copy()).cuda(); Fb = torch.tensor(F0[2:].copy()).cuda()
+    ops.ess_sweep(x, y, Fa, H0, it=5, seed=11, chain0=0)
+    ops.ess_sweep(x, y, Fb, H0[2:], it=5, seed=11, chain0=2)
+    assert np.array_equal(Fa.cpu().numpy()[2:], Fb.cpu().numpy()) and not np.array_equal(Fa.cpu().numpy(), F0)
+
+
 def test_elliptical_slice_contract(gp):
+    """The drop-in function (global numpy stream in, fresh array out): the stream is left where the reference leaves it
+    (N normals, slice level, angle, one uniform per rejected proposal)."""
     n = 120
     x, y = gp.synthetic.ih45_series(n)
     hyp = np.array([5.0, 4.0, 2.5])
     f = 0.8 * (y - y.mean())
     np.random.seed(9)
     pf = gp.kcMCMC.sliceSample.elliptical_slice(f, x, y, hyp)
+    after = np.random.random_sample()
     assert pf.shape == f.shape and np.all(np.isfinite(pf)) and not np.array_equal(pf, f)
     lik = gp.kcGP.likK.TruncatedGauss2(upper=100 - y.mean(), lower=-y.mean(), log_sigma=np.log(hyp[2]))
     assert np.isfinite(lik.evaluate(y=y - y.mean(), mu=pf))
+    # replay on the oracle with the same stream: same proposal count, same f'
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import EssTape
+    rs = np.random.RandomState(9)
+    zz, u, th = rs.standard_normal(n), rs.random_sample(), None
+    state = rs.get_state()
+    th = rs.random_sample(256)
+    of, trips = so.elliptical_slice(f, x, y, hyp, EssTape(so.ess_nu_from_z(x, hyp, zz), u, th))
+    rs.set_state(state)
+    rs.random_sample(trips)
+    assert after == rs.random_sample()
+    np.testing.assert_allclose(pf, of, rtol=1e-8, atol=1e-8)
 
 
 def test_framework_loop_matches_oracle_on_the_global_stream(gp, tmp_path):

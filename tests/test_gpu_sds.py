@@ -407,3 +407,58 @@ def test_resident_loop_equals_wave_loop(gp):
     _lib.load().gpmc_sds_loop_stats(ctypes.byref(r), ctypes.byref(i), ctypes.byref(l))
     print('resident loop, last call: %d rounds queued, %d found nothing to do, %d ladder passes' % (r.value, i.value, l.value))
     assert r.value >= 2
+
+
+def test_run_mode_equals_a_sequence_of_sweeps(gp):
+    """gpmc_sds_run (many iterations per call, every chain advancing on its own inside the resident loop) against the
+    same iterations done one gpmc_sds_sweep call at a time: Philox is keyed by (seed, chain, iteration), so states and
+    history must agree bit for bit -- across the iter == 500 switch, with fewer slots than chains (chains that continue
+    and chains that are admitted share rounds), and with the f history kept every other iteration."""
+    import torch
+    from gpmc_b200 import ops
+    n, B, iters, it0 = 120, 13, 5, 497
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    F = torch.tensor(F0.copy()).cuda(); H = torch.tensor(H0.copy()).cuda()
+    ref_h, ref_ll, ref_nt, ref_f = [], [], [], []
+    for k in range(iters):
+        nt, ll, st = ops.sds_sweep(x, y, F, H, scale, it0 + k, seed=5, chain0=3, max_trips=48)
+        assert int((st != 0).sum().item()) == 0
+        ref_h.append(H.cpu().numpy().copy()); ref_ll.append(ll.cpu().numpy().copy()); ref_nt.append(nt.cpu().numpy().copy())
+        ref_f.append(F.cpu().numpy().copy())
+    for wave in (None, 4):
+        F2 = torch.tensor(F0.copy()).cuda(); H2 = torch.tensor(H0.copy()).cuda()
+        hh, hl, ht, hf, n_exh = ops.sds_run(x, y, F2, H2, scale, it0, iters, seed=5, chain0=3, max_trips=48, chains_per_wave=wave,
+                                            keep_f_every=2, workspace=ops.Workspace())
+        assert n_exh == 0
+        assert np.array_equal(F2.cpu().numpy(), ref_f[-1]) and np.array_equal(H2.cpu().numpy(), ref_h[-1])
+        hh, hl, ht, hf = hh.cpu().numpy(), hl.cpu().numpy(), ht.cpu().numpy(), hf.cpu().numpy()
+        for k in range(iters):
+            assert np.array_equal(hh[:, k, :], ref_h[k]) and np.array_equal(hl[:, k], ref_ll[k]) and np.array_equal(ht[:, k], ref_nt[k])
+        assert hf.shape == (B, 3, n)
+        for j, k in enumerate((0, 2, 4)):
+            assert np.array_equal(hf[:, j, :], ref_f[k])
+
+
+def test_run_mode_counts_exhausted_transitions(gp):
+    """A trip budget of 1: most transitions run out of proposals, keep their state for that iteration (the recorded sample
+    is the unchanged theta) and are counted; the run still finishes every iteration of every chain."""
+    import torch
+    from gpmc_b200 import ops
+    n, B, iters = 64, 6, 4
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    F = torch.tensor(F0.copy()).cuda(); H = torch.tensor(H0.copy()).cuda()
+    hh, hl, ht, hf, n_exh = ops.sds_run(x, y, F, H, scale, 0, iters, seed=2, max_trips=1)
+    ht, hh = ht.cpu().numpy(), hh.cpu().numpy()
+    assert np.all(ht == 1) and n_exh > 0
+    prev = H0.copy()
+    changed = 0
+    for k in range(iters):
+        same = np.all(hh[:, k, :] == prev, axis=1)
+        changed += int((~same).sum())
+        prev = hh[:, k, :]
+    assert changed + n_exh == B * iters
+    assert np.array_equal(H.cpu().numpy(), hh[:, -1, :])

@@ -35,3 +35,15 @@ def test_multivariate_normal_draw_is_f_plus_sd_z():
     np.random.seed(7)
     z = np.random.standard_normal(n)
     np.testing.assert_allclose(g, f + 1.2 * z, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize('n,seed', [(40, 5), (120, 6)])
+def test_elliptical_slice_restatement_is_bit_identical_to_literal(n, seed):
+    x, y = mg._series(n)
+    rs = np.random.RandomState(seed)
+    hyp = np.array([4., 5., 1.8])
+    f = 0.7 * (y - y.mean())
+    tape = rl.EssTape(so.ess_nu_from_z(x, hyp, rs.standard_normal(n)), rs.random_sample(), rs.random_sample(64))
+    pf, trips = rl.run_literal_ess_with_tape(f, x, y, hyp, tape)
+    of, otrips = so.elliptical_slice(f, x, y, hyp, tape)
+    assert trips == otrips and np.array_equal(pf, of)
