@@ -404,6 +404,7 @@ int gpmc_set_tuning(int key, int value)
     if (key == 5) { set_trsm_blocks_per_cta(value); return 0; }
     if (key == 6) { set_sds_mode(value); return 0; }
     if (key == 7) { set_sds_runahead(value); return 0; }
+    if (key == 8) { set_sds_literal(value); return 0; }
     return GPMC_EINVAL;
 }
 

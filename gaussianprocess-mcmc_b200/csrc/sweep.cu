@@ -28,7 +28,8 @@ namespace gpmc {
 
 struct SweepBuffers {
     int n, ld, ldv, P, nt, cap;                  // cap = chains per wave
-    long long mat;                               // doubles per matrix slot: n rows + the border row that carries g
+    long long mat;                               // doubles per slot of buf2 (and of buf1 in the reduced form): n rows + the border row that carries g
+    long long mat1;                              // doubles per slot of buf1: (n + 1) rows, or (2n + 1) in the literal form (K rides below g)
     double *buf1, *buf2, *Wsave, *Wtmp;
     double *Fin, *Fout, *g, *svec, *fprop, *z, *m, *eta;          // [cap, ldv]
     double *theta, *hyp_min, *hyp_max, *hyp_in, *hyp_out;         // [cap, P]
@@ -37,6 +38,10 @@ struct SweepBuffers {
     int *chain_of, *phase, *parked, *resolved, *map_new, *map_act, *iter_of;   // resident loop (sds.cuh)
     int *count_new, *count_act, *status_word, *next_chain;           // (inside the 256-byte block of `count`)
 };
+
+// R = K - V^T V (sliceSample.py:197-198) formed as the reference writes it (gpmc_set_tuning(8, 1)) instead of the reduced form
+static int g_sds_literal = 0;
+void set_sds_literal(int v) { g_sds_literal = v ? 1 : 0; }
 
 static char *carve(char *&p, size_t bytes) { char *r = p; p += align_up(bytes, 256); return r; }
 
@@ -47,8 +52,9 @@ static size_t layout(SweepBuffers &w, char *base, int n, int P, int cap)
     char *p = base;
     w.n = n; w.ld = ld_for(n); w.ldv = w.ld; w.P = P; w.nt = (n + NB - 1) / NB; w.cap = cap;
     w.mat = (long long)(n + 1) * w.ld;
+    w.mat1 = g_sds_literal ? (long long)(2 * n + 1) * w.ld : w.mat;
     const size_t mat = (size_t)w.mat * 8;
-    w.buf1 = (double *)carve(p, mat * cap);
+    w.buf1 = (double *)carve(p, (size_t)w.mat1 * 8 * cap);
     w.buf2 = (double *)carve(p, mat * cap);
     w.Wsave = (double *)carve(p, (size_t)w.nt * NB * NB * 8 * cap);
     w.Wtmp = (double *)carve(p, (size_t)NB * NB * 8 * cap);
@@ -123,6 +129,111 @@ static int mark_not_pd(const AuxCtx &c, int *info_dev, const std::vector<int> &i
     return 0;
 }
 
+// ---- literal form of the posterior covariance (sliceSample.py:197-198,204), for parity with the reference as written:
+//   V = solve(L, K)          K rides through the factorisation of K+S as n MORE border rows (rows n+1 .. 2n of the slot,
+//                            below g): the update GEMMs and panel solves leave X = K L^-T = V^T there -- a backward
+//                            stable triangular solve with n right-hand sides on DMMA, no explicit inverse
+//   R = K - V^T V            K assembled again into the second buffer, minus X X^T by the DMMA tile kernel (lower tiles)
+//   m = (R inv(S)) g         symmetric matrix-vector product from the lower triangle
+//   C = chol(R + 1e-11 I)
+// 8/3 N^3 flop per evaluation instead of 4/3 N^3; used for parity (gpmc_set_tuning(8, 1)), not for speed.
+__global__ void __launch_bounds__(256)
+symv_lower_kernel(BatchView R, int n, const double *__restrict__ g, const double *__restrict__ svec, int ldv, double *__restrict__ out)
+{
+    // out[i] = sum_j Rsym[i][j] * (g[j] / S[j]) for the 32 rows i = k0 .. k0+31; Rsym from the lower triangle of R
+    const int b = blockIdx.y;
+    if (R.count && b >= *R.count) return;
+    const int m = batch_item(R, b);
+    const double *Rb = R.base + (size_t)m * R.stride;
+    const double *gv = g + (size_t)m * ldv, *sv = svec + (size_t)m * ldv;
+    const int k0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ double part_col[8][32], part_row[32];
+    // strict-upper part, column-wise: entry (i, j), j > i, is R[j][i]; lane = column i, warps stride the rows j
+    double acc = 0.0;
+    const int i = k0 + lane;
+    for (int j = k0 + warp; j < n; j += 8)
+        if (i < n && j > i) acc = fma(Rb[(size_t)j * R.ld + i], (1.0 / sv[j]) * gv[j], acc);
+    part_col[warp][lane] = acc;
+    // lower part incl. the diagonal, row-wise: warp w takes rows k0 + 4w .. k0 + 4w + 3
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = k0 + warp * 4 + rr;
+        double a = 0.0;
+        if (r < n) {
+            const double *row = Rb + (size_t)r * R.ld;
+            for (int j = lane; j <= r; j += 32) a = fma(row[j], (1.0 / sv[j]) * gv[j], a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) part_row[warp * 4 + rr] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && k0 + threadIdx.x < n) {
+        double v = part_row[threadIdx.x];
+        for (int w8 = 0; w8 < 8; ++w8) v += part_col[w8][threadIdx.x];
+        out[(size_t)m * ldv + k0 + threadIdx.x] = v;
+    }
+}
+
+__global__ void add_diag_const_kernel(BatchView A, int n, double v)
+{
+    const int b = blockIdx.y;
+    if (A.count && b >= *A.count) return;
+    const int m = batch_item(A, b);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A.base[(size_t)m * A.stride + (size_t)i * A.ld + i] += v;
+}
+
+// Assemble K+S (+ jitter) with its border rows into the slots of V1: g below the matrix, and in the literal form K
+// itself below g.
+static int aux_fill(const AuxCtx &c, BatchView V1, int nitems, const double *jit)
+{
+    SweepBuffers &w = *c.w;
+    int rc;
+    if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, jit, V1, nitems, c.s))) return rc;
+    if ((rc = border_set(V1, w.n, w.g, w.ldv, nitems, c.s))) return rc;
+    if (g_sds_literal) {
+        BatchView Krows{V1.base + (size_t)(w.n + 1) * w.ld, V1.stride, V1.ld, V1.map, V1.count};
+        if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, 0, nullptr, Krows, nitems, c.s))) return rc;     // full K, no S
+    }
+    return 0;
+}
+static int aux_border_rows(const SweepBuffers &w) { return g_sds_literal ? 1 + w.n : 1; }
+
+// R (+ 1e-11 I) into V2 from the factored slot V1
+static int aux_form_R(const AuxCtx &c, BatchView V1, BatchView V2, int nitems, bool with_m)
+{
+    SweepBuffers &w = *c.w;
+    cudaStream_t s = c.s;
+    int rc;
+    if (!g_sds_literal) {
+        // U = L^-T is already in V1;  R = S - S U U^T S + 1e-11 I (:197-198,205)
+        return r_sequence(V2, V1, w.n, nitems, w.svec, w.ldv, s);
+    }
+    // R = K - X X^T with X = K L^-T in rows n+1 .. 2n of V1 (:197-198)
+    if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_LOWER_ONLY, nullptr, V2, nitems, s))) return rc;
+    GemmArgs g{};
+    g.C = V2;
+    g.A = Operand{V1.base + (size_t)(w.n + 1) * w.ld, V1.stride, V1.ld};
+    g.B = g.A;
+    g.cr0 = 0; g.cc0 = 0; g.rows = w.n; g.cols = w.n;
+    g.ar0 = 0; g.br0 = 0; g.k0 = 0; g.bk0 = 0; g.klen = w.n;
+    g.lower_only = 1;
+    g.epi = EPI_SUB;
+    g.skip_upper = 1;
+    if ((rc = launch_gemm(g, nitems, KC_SYRK_R, s))) return rc;
+    if (with_m) {
+        // m = (R inv(S)) g (:204), before the 1e-11 goes onto the diagonal
+        prof_begin(KC_VEC, s);
+        symv_lower_kernel<<<dim3((w.n + 31) / 32, nitems), 256, 0, s>>>(V2, w.n, w.g, w.svec, w.ldv, w.m);
+        prof_end(KC_VEC, s);
+        GPMC_LAUNCH_CHECK();
+    }
+    add_diag_const_kernel<<<dim3((w.n + 255) / 256, nitems), 256, 0, s>>>(V2, w.n, 1e-11);      // :205
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
 // From a factored K+S (V1: L in the lower triangle, z in the border row up to its last block) to C = chol(R + 1e-11 I)
 // in V2, for the items of the views:
 static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitems)
@@ -131,13 +242,19 @@ static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitem
     cudaStream_t s = c.s;
     const long long strideW = (long long)w.nt * NB * NB;
     int rc;
-    // ---- z = L^-1 g and the log marginal (:147)
-    if ((rc = border_finish(V1, w.n, w.G, w.info1, nitems, s))) return rc;
-    if ((rc = border_get(V1, w.n, w.z, w.ldv, w.info1, nitems, s))) return rc;
-    // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
-    if ((rc = inverse_sequence(V1, w.n, nitems, w.Wsave, strideW, s))) return rc;
-    if ((rc = launch_trmv(V1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, nitems, s))) return rc;
-    if ((rc = r_sequence(V2, V1, w.n, nitems, w.svec, w.ldv, s))) return rc;
+    if (g_sds_literal) {
+        // several border rows: z = L^-1 g is complete in row n (the last block column was solved with the others)
+        if ((rc = launch_quad_logdet(V1, w.n, V1.base + (size_t)w.n * w.ld, (int)V1.stride, w.G, w.info1, nitems, s))) return rc;   // :147
+        if ((rc = aux_form_R(c, V1, V2, nitems, true))) return rc;
+    } else {
+        // ---- z = L^-1 g and the log marginal (:147)
+        if ((rc = border_finish(V1, w.n, w.G, w.info1, nitems, s))) return rc;
+        if ((rc = border_get(V1, w.n, w.z, w.ldv, w.info1, nitems, s))) return rc;
+        // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
+        if ((rc = inverse_sequence(V1, w.n, nitems, w.Wsave, strideW, s))) return rc;
+        if ((rc = launch_trmv(V1, w.n, 1, 1, w.z, w.g, w.svec, w.ldv, w.m, nitems, s))) return rc;
+        if ((rc = aux_form_R(c, V1, V2, nitems, true))) return rc;
+    }
     // ---- C = chol(R + 1e-11 I) (jitchol, :205)
     if ((rc = fill_int_mapped(w.info2, 0, V1.map, V1.count, nitems, s))) return rc;
     return potrf_sequence(V2, w.n, nitems, w.info2, w.Wtmp, NB * NB, 0, 0, s);
@@ -154,17 +271,15 @@ static int aux_queue(const AuxCtx &c, int na)
     SweepBuffers &w = *c.w;
     cudaStream_t s = c.s;
     if (na <= 0) return 0;
-    const long long mat = w.mat;
-    BatchView A1{w.buf1, mat, w.ld, w.map, w.count};
-    BatchView A2{w.buf2, mat, w.ld, w.map, w.count};
+    BatchView A1{w.buf1, w.mat1, w.ld, w.map, w.count};
+    BatchView A2{w.buf2, w.mat, w.ld, w.map, w.count};
     const long long strideW = (long long)w.nt * NB * NB;
     int rc;
     // ---- K+S and its Cholesky factor (jitchol, :196); g rides through the factorisation as a border row:
     //      z = L^-1 g comes out of the update GEMMs and panel solves
     if ((rc = fill_int_mapped(w.info1, 0, w.map, w.count, na, s))) return rc;
-    if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, nullptr, A1, na, s))) return rc;
-    if ((rc = border_set(A1, w.n, w.g, w.ldv, na, s))) return rc;
-    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
+    if ((rc = aux_fill(c, A1, na, nullptr))) return rc;
+    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w)))) return rc;
     return aux_downstream(c, A1, A2, na);
 }
 
@@ -174,7 +289,7 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     cudaStream_t s = c.s;
     const int na = (int)active.size();
     if (na == 0) return 0;
-    const long long mat = w.mat;
+    const long long mat = w.mat, mat1 = w.mat1;
     const long long strideW = (long long)w.nt * NB * NB;
     int rc;
     if ((rc = aux_queue(c, na))) return rc;
@@ -210,11 +325,10 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
             GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
             GPMC_CUDA_CHECK(cudaMemcpyAsync(w.jit, jit.data(), w.cap * 8, cudaMemcpyHostToDevice, s));
-            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            BatchView F1{w.buf1, mat1, w.ld, w.fmap, cnt};
             if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
-            if ((rc = launch_cov_assemble(c.x, c.N, c.D, w.theta, c.P, c.n_ell, GPMC_ASM_ADD_S | GPMC_ASM_LOWER_ONLY, w.jit, F1, nf, s))) return rc;
-            if ((rc = border_set(F1, w.n, w.g, w.ldv, nf, s))) return rc;
-            if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, 1))) return rc;
+            if ((rc = aux_fill(c, F1, nf, w.jit))) return rc;
+            if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w)))) return rc;
             std::vector<int> still, tmp;
             if ((rc = failed_items(c, w.info1, todo, still, tmp))) return rc;
             for (int id : todo) if (tmp[id] == 0) recovered.push_back(id);
@@ -229,7 +343,7 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             const int nr = (int)recovered.size();
             GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, recovered.data(), nr * 4, cudaMemcpyHostToDevice, s));
             GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nr, 4, cudaMemcpyHostToDevice, s));
-            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            BatchView F1{w.buf1, mat1, w.ld, w.fmap, cnt};
             BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
             if ((rc = aux_downstream(c, F1, F2, nr))) return rc;
             std::vector<int> bad2, tmp;
@@ -251,9 +365,9 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             const int nf = (int)todo.size();
             GPMC_CUDA_CHECK(cudaMemcpyAsync(w.fmap, todo.data(), nf * 4, cudaMemcpyHostToDevice, s));
             GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nf, 4, cudaMemcpyHostToDevice, s));
-            BatchView F1{w.buf1, mat, w.ld, w.fmap, cnt};
+            BatchView F1{w.buf1, mat1, w.ld, w.fmap, cnt};
             BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
-            if ((rc = r_sequence(F2, F1, w.n, nf, w.svec, w.ldv, s))) return rc;      // rebuild R + 1e-11 I
+            if ((rc = aux_form_R(c, F1, F2, nf, false))) return rc;                   // rebuild R + 1e-11 I
             if (first) {
                 if ((rc = diag_stats(F2, w.n, w.mean, w.bad, nf, s))) return rc;
                 GPMC_CUDA_CHECK(cudaMemcpyAsync(mean.data(), w.mean, w.cap * 8, cudaMemcpyDeviceToHost, s));
@@ -571,7 +685,7 @@ int gpmc_sds_run(const double *x_dev, const double *y_dev, int N, int D, double 
     SweepBuffers w;
     layout(w, (char *)ws_dev, N, P, cap);
     if (w.ld != N) {
-        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(w.mat1 / w.ld) * cap, s));
         GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
     }
     RunSpec run;
@@ -615,7 +729,7 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
     // pad columns of the matrices must be zero (the DMMA kernels contract over multiples of 16)
     // (every slot has N + 1 rows -- the border row included -- and the slots are contiguous)
     if (w.ld != N) {
-        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
+        GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf1 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(w.mat1 / w.ld) * cap, s));
         GPMC_CUDA_CHECK(cudaMemset2DAsync(w.buf2 + N, (size_t)w.ld * 8, 0, (size_t)(w.ld - N) * 8, (size_t)(N + 1) * cap, s));
     }
     if (g_sds_mode == 0)

@@ -237,7 +237,11 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  * key 5: 64-row blocks one CTA of the panel solve takes: 0 = auto (1, 2 or 4 by launch size), else forced.
  * key 6: gpmc_sds_sweep loop: 0 = resident loop (slots refilled on the device, host polls a status word without
  *        synchronising; default), 1 = wave loop (one status read per trip, waves drained to their slowest chain).
- * key 7: rounds the resident loop queues ahead of the last status word it has seen (0 = auto: 2..4 by problem size). */
+ * key 7: rounds the resident loop queues ahead of the last status word it has seen (0 = auto: 2..4 by problem size).
+ * key 8: form of the posterior covariance inside gpmc_sds_sweep / gpmc_sds_run: 0 = reduced, R = S - S (K+S)^-1 S (4/3 N^3
+ *        flop per evaluation; default), 1 = literal, V = solve(L, K), R = K - V^T V, m = (R inv(S)) g exactly as
+ *        sliceSample.py:197-198,204 write it (8/3 N^3; twice the workspace per chain -- query gpmc_sds_workspace_bytes
+ *        after setting it).  Used for parity with the reference, not for speed. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:

@@ -462,3 +462,55 @@ def test_run_mode_counts_exhausted_transitions(gp):
         prev = hh[:, k, :]
     assert changed + n_exh == B * iters
     assert np.array_equal(H.cpu().numpy(), hh[:, -1, :])
+
+
+@pytest.mark.parametrize('path', SDS, ids=[os.path.basename(p) for p in SDS])
+def test_literal_R_mode_matches_reference(gp, path):
+    """gpmc_set_tuning(8, 1): V = solve(L, K), R = K - V^T V, m = (R inv(S)) g formed as sliceSample.py:197-198,204 write
+    them (K rides through the factorisation of K+S as n more border rows).  theta', trips and log N(g) exact as in the
+    default form; f' is now compared with the reference's own f' at the resolution the LITERAL algorithm has: the spread
+    between two CPU evaluations of the literal form that differ only in BLAS summation order (1 thread vs all threads),
+    measured here per fixture, with a floor of 1e-6."""
+    import threadpoolctl
+    from gpmc_b200 import ops
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    z = np.load(path)
+    ops.set_tuning(8, 1)
+    try:
+        import torch
+        F = torch.tensor(z['f'][None].copy()).cuda()
+        H = torch.tensor(z['hyp'][None].copy()).cuda()
+        tape = ops.Tape(z['z'][None], z['v'][None], [float(z['u0'])], z['U'][None])
+        nt, ll, st = ops.sds_sweep(z['x'], z['y'], F, H, z['scale'], int(z['it']), tape=tape, workspace=ops.Workspace())
+        f, h = F.cpu().numpy()[0], H.cpu().numpy()[0]
+    finally:
+        ops.set_tuning(8, 0)
+    assert int(st.item()) == 0 and int(nt.item()) == int(z['ref_trips'])
+    np.testing.assert_allclose(h, z['ref_prop_hyp'], rtol=RTOL_HYP, atol=0)
+    ref = float(z['trace_propG'][int(nt.item()) - 1])
+    assert abs(float(ll.item()) - ref) <= RTOL_LL * abs(ref)
+    # the resolution of the literal algorithm: (a) BLAS summation order (1 thread vs all threads -- no effect at small N,
+    # where OpenBLAS does not split the products), (b) one-ulp noise on the entries of K (two correct exp() implementations
+    # differ by that much): how far the reference's own f' moves under either
+    with threadpoolctl.threadpool_limits(limits=1):
+        f1, h1 = so.surrogate_slice_sampling(z['f'], z['x'], z['y'], z['hyp'], z['scale'], int(z['it']),
+                                             Tape(z['z'], z['v'], z['u0'], z['U']), r_form='literal')
+    real_cov = so.cov_matrix
+    rs = np.random.RandomState(1)
+
+    def ulp_cov(x, hyp):
+        K = real_cov(x, hyp)
+        E = np.triu(rs.choice([-1.0, 0.0, 1.0], size=K.shape), 1)
+        return K * (1.0 + 2.220446049250313e-16 * (E + E.T))
+    so.cov_matrix = ulp_cov
+    try:
+        f2, h2 = so.surrogate_slice_sampling(z['f'], z['x'], z['y'], z['hyp'], z['scale'], int(z['it']),
+                                             Tape(z['z'], z['v'], z['u0'], z['U']), r_form='literal')
+    finally:
+        so.cov_matrix = real_cov
+    spread = max(float(np.abs(f1 - z['ref_prop_f']).max()), float(np.abs(f2 - z['ref_prop_f']).max()) if np.array_equal(h2, z['ref_prop_hyp']) else 0.0)
+    err = float(np.abs(f - z['ref_prop_f']).max())
+    print('%s: literal-R device |f - f_ref| %.2e; reference resolution (BLAS order / 1-ulp K) %.2e; |f| ~ %.2f' % (
+        os.path.basename(path), err, spread, np.abs(z['ref_prop_f']).max()))
+    assert err <= max(1e-6, 20.0 * spread), (err, spread)
