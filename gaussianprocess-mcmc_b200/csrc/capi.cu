@@ -100,11 +100,11 @@ static LoglikLayout loglik_layout(int N, int B)
 // rows; `diag_value` is the (constant) diagonal of an item's matrix from its hyper-parameter row.
 int factor_wave(const std::function<int(BatchView, int, const double *)> &fill, const std::function<double(const double *)> &diag_value,
                 BatchView A, int N, int nb, const double *hyp_w, int P, int *info_w, double *W, double *jit_dev, int *map_dev,
-                int jitter_policy, int border_rows, cudaStream_t s)
+                int jitter_policy, int border_rows, cudaStream_t s, int fuse)
 {
     int rc = fill(A, nb, nullptr);
     if (rc) return rc;
-    if ((rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s, border_rows))) return rc;
+    if ((rc = potrf_sequence(A, N, nb, info_w, W, NB * NB, 0, 0, s, border_rows, fuse))) return rc;
     if (jitter_policy != GPMC_JITTER_PYGPS) return 0;
     std::vector<int> info(nb);
     GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -131,7 +131,7 @@ int factor_wave(const std::function<int(BatchView, int, const double *)> &fill, 
         GPMC_CUDA_CHECK(cudaMemcpyAsync(info_w, info.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
         BatchView Am{A.base, A.stride, A.ld, map_dev, nullptr};
         if ((rc = fill(Am, nf, jit_dev))) return rc;
-        if ((rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s, border_rows))) return rc;
+        if ((rc = potrf_sequence(Am, N, nf, info_w, W, NB * NB, 0, 0, s, border_rows, fuse))) return rc;
         GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_w, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         GPMC_CUDA_CHECK(cudaStreamSynchronize(s));
         std::vector<int> still;
@@ -216,7 +216,8 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     BatchView A{A_dev, (long long)N * ld, ld, nullptr, nullptr};
     { int rc0 = fill_int(info_dev, 0, B, s); if (rc0) return rc0; }
 
-    if (jitter_policy != GPMC_JITTER_PYGPS) return potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s);
+    const int fuse = potrf_fuse_auto(N, B, 0);
+    if (jitter_policy != GPMC_JITTER_PYGPS) return potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s, 0, fuse);
 
     // pyGPs jitchol: keep a copy, try once, then the jitter ladder on the items that failed.
     double *backup = (double *)wp; wp += mat_bytes;
@@ -225,7 +226,7 @@ int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int j
     int *map_dev = (int *)wp; wp += align_up((size_t)B * sizeof(int), 256);
     int *bad_dev = (int *)wp;
     GPMC_CUDA_CHECK(cudaMemcpyAsync(backup, A_dev, mat_bytes, cudaMemcpyDeviceToDevice, s));
-    int rc = potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s);
+    int rc = potrf_sequence(A, N, B, info_dev, W, NB * NB, 0, zero_upper, s, 0, fuse);
     if (rc) return rc;
     std::vector<int> info(B);
     GPMC_CUDA_CHECK(cudaMemcpyAsync(info.data(), info_dev, B * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -307,10 +308,11 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
             return border_set(V, N, g_w, N, nitems, s);
         };
         auto diag = [&](const double *h) { return host_diag_value(h, n_ell); };
-        int rc = factor_wave(fill, diag, A, N, nb, hyp_w, P, info_w, W, jit_dev, map_dev, jitter_policy, 1, s);
+        const int fuse = potrf_fuse_auto(N, nb, 1);
+        int rc = factor_wave(fill, diag, A, N, nb, hyp_w, P, info_w, W, jit_dev, map_dev, jitter_policy, 1, s, fuse);
         if (rc) return rc;
         // z = L^-1 g sits in the border row except for the last column block: finish it, then quad form + log det
-        rc = border_finish(A, N, loglik_dev + s0, info_w, nb, s);
+        rc = border_finish(A, N, loglik_dev + s0, info_w, nb, s, fuse);
         if (rc) return rc;
     }
     return 0;
@@ -405,6 +407,7 @@ int gpmc_set_tuning(int key, int value)
     if (key == 6) { set_sds_mode(value); return 0; }
     if (key == 7) { set_sds_runahead(value); return 0; }
     if (key == 8) { set_sds_literal(value); return 0; }
+    if (key == 9) { set_panel_fuse(value); return 0; }
     return GPMC_EINVAL;
 }
 

@@ -122,6 +122,10 @@ int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, 
 // factored in 16 steps of 8 columns (the default panel factor kernel)
 int launch_potf2_reg(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                      int B, cudaStream_t s);
+// potf2_reg.cu : panel factor AND panel solve of block column j0 in one launch (n_rows = n + border rows; in the last block
+// column the border rows are solved too) -- for many small matrices in flight
+int launch_panel_fused(BatchView A, int n, int n_rows, int j0, double *W, long long strideW, int *info, int zero_upper,
+                       int B, cudaStream_t s);
 void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on
 void set_potrf_window(int w);      // override the window of the windowed schedule (multiple of NB; 0 = default)
 void set_potf2_mode(int mode);     // 0: register-resident kernel (default), 2: the shared-memory lite kernel, 1: always the full-inverse one
@@ -157,6 +161,7 @@ int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const 
 
 // sweep.cu
 void set_sds_mode(int mode);       // 0: resident loop (default), 1: wave loop
+void set_panel_fuse(int mode);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
 void set_sds_literal(int v);       // 1: R = K - V^T V as the reference writes it (parity), 0: reduced form (default)
 void set_sds_runahead(int r);      // rounds queued ahead of the last status word seen (0: auto)
 void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);

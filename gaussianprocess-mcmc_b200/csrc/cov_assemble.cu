@@ -19,6 +19,7 @@ namespace gpmc {
 
 constexpr int AT = 64;          // tile edge
 constexpr int AT_PAD = 66;      // smem row stride (doubles): keeps double2 stores 16 B aligned
+constexpr int ASM_TPC = 1;      // tiles per CTA (4 was measured: N=4096 x 256 4.17 -> 4.69 ms, slower -- the per-CTA scalar prologue is not the limiter)
 
 // DT > 0: input dimension known at compile time (the distance loop unrolls and the column values live in registers);
 // DT == 0: generic D.  The kernel is instruction-issue bound (ncu: 79 % issue slots, FP64 pipe 47 %, DRAM 33 %), so the
@@ -33,14 +34,6 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
     const int b = blockIdx.y;
     if (A.count && b >= *A.count) return;
     const int m = batch_item(A, b);
-
-    // tile decode: t -> (tm >= tn)
-    const int t = blockIdx.x;
-    int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
-    while (tm * (tm + 1) / 2 > t) --tm;
-    const int tn = t - tm * (tm + 1) / 2;
-    const int r0 = tm * AT, c0 = tn * AT;
 
     __shared__ double s_ell[MAX_ELL];
     __shared__ double s_ui[MAX_ELL][AT];
@@ -74,6 +67,27 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
         } else s_scal[3] = 1.0;
     }
     __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const double sf2 = s_scal[0];
+    const double diag_add = s_scal[1], jit = s_scal[2], sn2 = s_scal[3];
+    const bool pred = (flags & GPMC_ASM_PRED) != 0;
+    const bool has_jit = (jitter != nullptr);
+    double *Ab = A.base + (size_t)m * A.stride;
+    const int cl = 2 * lane;
+    const int nt1 = (N + AT - 1) / AT, ntiles = nt1 * (nt1 + 1) / 2;
+    // A CTA takes ASM_TPC consecutive tiles of its matrix (experiment: amortise the per-item scalars above -- two
+    // exp(log(.)) round trips and the S_ii expression on one or two threads while the rest of the CTA waits; ncu r02f shows
+    // barrier stalls of 2.6 per issue -- over several tiles.  Measured slower with 4, so the default is 1.)
+    for (int tt = 0; tt < ASM_TPC; ++tt) {
+    // tile decode: t -> (tm >= tn)
+    const int t = blockIdx.x * ASM_TPC + tt;
+    if (t >= ntiles) break;
+    int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+    while (tm * (tm + 1) / 2 > t) --tm;
+    const int tn = t - tm * (tm + 1) / 2;
+    const int r0 = tm * AT, c0 = tn * AT;
+    if (tt > 0) __syncthreads();                 // the previous tile's u vectors / mirrored tile are still being read
     // u = x / ell for the tile's rows and columns
     for (int e = tid; e < 2 * AT * D; e += 256) {
         const int which = e / (AT * D);
@@ -86,13 +100,6 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
     }
     __syncthreads();
 
-    const int warp = tid >> 5, lane = tid & 31;
-    const double sf2 = s_scal[0];
-    const double diag_add = s_scal[1], jit = s_scal[2], sn2 = s_scal[3];
-    const bool pred = (flags & GPMC_ASM_PRED) != 0;
-    const bool has_jit = (jitter != nullptr);
-    double *Ab = A.base + (size_t)m * A.stride;
-    const int cl = 2 * lane;
     const int gc = c0 + cl;
     const bool mirror = (tm != tn) && !(flags & GPMC_ASM_LOWER_ONLY);
 
@@ -146,7 +153,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
         }
     }
     }
-    if (!mirror) return;
+    if (!mirror) continue;
     __syncthreads();
     // mirrored tile: rows c0.., cols r0..
 #pragma unroll
@@ -162,6 +169,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
             else if (gcol < N)   dst[0] = k0;
         }
     }
+    }
 }
 
 int launch_cov_assemble(const double *x, int N, int D, const double *hyp, int P, int n_ell, int flags,
@@ -170,7 +178,7 @@ int launch_cov_assemble(const double *x, int N, int D, const double *hyp, int P,
     if (D > MAX_ELL || n_ell > MAX_ELL) { set_error("D=%d exceeds MAX_ELL=%d", D, MAX_ELL); return GPMC_EINVAL; }
     if (B <= 0) return 0;
     const int nt = (N + AT - 1) / AT;
-    dim3 grid(nt * (nt + 1) / 2, B);
+    dim3 grid((nt * (nt + 1) / 2 + ASM_TPC - 1) / ASM_TPC, B);
     prof_begin(KC_ASSEMBLE, s);
     switch (D) {
         case 1: cov_assemble_kernel<1><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;

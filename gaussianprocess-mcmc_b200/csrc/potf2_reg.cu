@@ -97,9 +97,23 @@ __device__ __forceinline__ void pick_slot(const double (&acc)[PR_SLOTS][2], int 
     switch (slot) { PR_PICK_ALL default: break; }
 }
 
+// FUSED = true: the panel SOLVE of the block column happens in the same launch (n_rows > n: border rows included; in the
+// last block column only the border rows are left to solve).  The factor's fragments and the 8x8 diagonal inverses are
+// kept in 76 KB of shared memory as dense 8x8 blocks (a lane's 16-byte B-operand loads of a block are 512 contiguous
+// bytes per warp: conflict free), and after the 16 factor steps every warp takes 8 rows at a time through the same
+// inverse-multiply + refinement chain as trsm_panel8.cu.  With one CTA per matrix and two CTAs per SM, one matrix's
+// latency-bound factor steps overlap the other's DMMA-bound solve -- which separate launches cannot do: every CTA of a
+// launch is in the same phase.  Used when many small matrices are in flight (potrf_sequence decides).
+constexpr int PF_LC_ELEMS = (PR_NF * (PR_NF + 1) / 2) * 64;      // lower 8x8 blocks of L11: block (R, C) at R (R + 1) / 2 + C
+constexpr int PF_SMEM = (PF_LC_ELEMS + PR_NF * 64) * (int)sizeof(double);
+
+template <bool FUSED>
 __global__ void __launch_bounds__(PR_THREADS, 2)
-potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info, int zero_upper)
+potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long strideW, int *__restrict__ info, int zero_upper, int n_rows)
 {
+    extern __shared__ __align__(16) double pf_dyn[];
+    double *Lc = pf_dyn;                                 // FUSED only
+    double *W8c = pf_dyn + PF_LC_ELEMS;
     __shared__ __align__(16) double sD[64];              // diagonal fragment on its way to the row-per-lane layout
     __shared__ __align__(16) double sL8[64], sW8[64];    // factor of the current diagonal fragment and its inverse (zeros above)
     __shared__ __align__(16) double sX[PR_NF][64];       // solved fragments X[block row][8][8] of the current block column
@@ -174,8 +188,11 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
             if (lane < 8) {
                 const int gr = b * 8 + r8;
 #pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2 *>(&sL8[r8 * 8 + c]) = make_double2((c <= r8) ? v[c] : 0.0, (c + 1 <= r8) ? v[c + 1] : 0.0);
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 lrow = make_double2((c <= r8) ? v[c] : 0.0, (c + 1 <= r8) ? v[c + 1] : 0.0);
+                    *reinterpret_cast<double2 *>(&sL8[r8 * 8 + c]) = lrow;
+                    if (FUSED) *reinterpret_cast<double2 *>(&Lc[(b * (b + 1) / 2 + b) * 64 + r8 * 8 + c]) = lrow;
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c <= r8 && gr < nv) Ab[(size_t)gr * ld + b * 8 + c] = v[c];
@@ -184,6 +201,7 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     sW8[c * 8 + r8] = v[c];                                         // W8[c][k = r8]; zero for c < k
+                    if (FUSED) W8c[b * 64 + c * 8 + r8] = v[c];
                     Wb[(size_t)(b * 8 + c) * NB + b * 8 + r8] = v[c];
                 }
             }
@@ -216,6 +234,7 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
                 dmma884_r(y0, y1, q1, wv.y);
                 xb0 = y0; xb1 = y1;
                 *reinterpret_cast<double2 *>(&sX[rowB][frag_off]) = make_double2(y0, y1);
+                if (FUSED) *reinterpret_cast<double2 *>(&Lc[(rowB * (rowB + 1) / 2 + b) * 64 + frag_off]) = make_double2(y0, y1);
                 {
                     const int gr = rowB * 8 + fr, gc = b * 8 + 2 * fk;
                     if (gr < nv) {
@@ -226,6 +245,7 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
                 if (slotA >= 0) {
                     xa0 = x0; xa1 = x1;
                     *reinterpret_cast<double2 *>(&sX[rowA][frag_off]) = make_double2(x0, x1);
+                    if (FUSED) *reinterpret_cast<double2 *>(&Lc[(rowA * (rowA + 1) / 2 + b) * 64 + frag_off]) = make_double2(x0, x1);
                     const int gr = rowA * 8 + fr, gc = b * 8 + 2 * fk;
                     if (gr < nv) {
                         if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(x0, x1);
@@ -250,6 +270,52 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
     if (tid == 0 && s_fail != 0) {
         if (info[m] == 0) info[m] = s_fail;
     }
+    if (FUSED) {
+        // ---------------------------------------------------------------- panel solve: X L11^T = A21 for the rows below
+        // (trsm_panel8.cu's chain; a warp owns 8 rows x 128 columns as accumulator fragments, 64 rows per pass of the CTA)
+        const int row_start = (j0 + NB < n) ? NB : n - j0;            // relative to the block's first row; last column: border rows only
+        const int rows_end = n_rows - j0;
+#pragma unroll 1
+        for (int row0 = row_start; row0 < rows_end; row0 += 8 * PR_WARPS) {
+            if (row0 + w * 8 >= rows_end) continue;                     // warp-uniform
+            const int r = row0 + w * 8 + fr;
+            const bool rv = r < rows_end;
+            double *grow = Ab + (size_t)min(r, rows_end - 1) * ld + 2 * fk;
+            double t[PR_NF][2];
+#pragma unroll
+            for (int b8 = 0; b8 < PR_NF; ++b8) {
+                double2 v = make_double2(0.0, 0.0);
+                if (rv && b8 * 8 + 2 * fk < nv) v = *reinterpret_cast<const double2 *>(grow + b8 * 8);
+                t[b8][0] = v.x;
+                t[b8][1] = v.y;
+            }
+#pragma unroll
+            for (int b8 = 0; b8 < PR_NF; ++b8) {
+                const double2 wv = *reinterpret_cast<const double2 *>(&W8c[b8 * 64 + frag_off]);
+                const double2 lv = *reinterpret_cast<const double2 *>(&Lc[(b8 * (b8 + 1) / 2 + b8) * 64 + frag_off]);
+                double x0 = 0.0, x1 = 0.0;
+                dmma884_r(x0, x1, t[b8][0], wv.x);                                  // X0 = A W8^T
+                dmma884_r(x0, x1, t[b8][1], wv.y);
+                double r0 = t[b8][0], r1 = t[b8][1];
+                dmma884_r(r0, r1, -x0, lv.x);                                       // r = A - X0 L8^T
+                dmma884_r(r0, r1, -x1, lv.y);
+                dmma884_r(x0, x1, r0, wv.x);                                        // X = X0 + r W8^T
+                dmma884_r(x0, x1, r1, wv.y);
+                const double nx0 = -x0, nx1 = -x1;
+#pragma unroll
+                for (int bp = b8 + 1; bp < PR_NF; ++bp) {
+                    const double2 lp = *reinterpret_cast<const double2 *>(&Lc[(bp * (bp + 1) / 2 + b8) * 64 + frag_off]);
+                    dmma884_r(t[bp][0], t[bp][1], nx0, lp.x);
+                    dmma884_r(t[bp][0], t[bp][1], nx1, lp.y);
+                }
+                if (rv) {
+                    const int c = b8 * 8 + 2 * fk;
+                    if (c + 1 < nv) *reinterpret_cast<double2 *>(grow + b8 * 8) = make_double2(x0, x1);
+                    else if (c < nv) grow[b8 * 8] = x0;
+                }
+            }
+        }
+    }
     if (zero_upper) {
         for (int e = tid; e < nv * nv; e += PR_THREADS) {
             const int r = e / nv, c = e - r * nv;
@@ -263,7 +329,21 @@ int launch_potf2_reg(BatchView A, int n, int j0, double *W, long long strideW, i
     if (B <= 0) return 0;
     if ((A.ld & 1) || (j0 & 1)) { set_error("potf2: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
     prof_begin(KC_POTF2, s);
-    potf2_reg_kernel<<<B, PR_THREADS, 0, s>>>(A, n, j0, W, strideW, info, zero_upper);
+    potf2_reg_kernel<false><<<B, PR_THREADS, 0, s>>>(A, n, j0, W, strideW, info, zero_upper, n);
+    prof_end(KC_POTF2, s);
+    GPMC_LAUNCH_CHECK();
+    return 0;
+}
+
+// panel factor + panel solve of block column j0 in one launch; n_rows = n + border rows
+int launch_panel_fused(BatchView A, int n, int n_rows, int j0, double *W, long long strideW, int *info, int zero_upper, int B, cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    if ((A.ld & 1) || (j0 & 1)) { set_error("panel: ld=%d j0=%d must be even", A.ld, j0); return GPMC_EALIGN; }
+    static DeviceOnce attr_set;
+    if (attr_set.first()) GPMC_CUDA_CHECK(cudaFuncSetAttribute(potf2_reg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    prof_begin(KC_POTF2, s);
+    potf2_reg_kernel<true><<<B, PR_THREADS, PF_SMEM, s>>>(A, n, j0, W, strideW, info, zero_upper, n_rows);
     prof_end(KC_POTF2, s);
     GPMC_LAUNCH_CHECK();
     return 0;

@@ -224,9 +224,23 @@ static LookAhead *lookahead_ctx()
 static int g_lookahead_mode = 0;       // 0 auto (B <= #SMs / 2), 1 off, 2 on
 void set_lookahead_mode(int mode) { g_lookahead_mode = mode; }
 
-int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
-                   int zero_upper_flag, cudaStream_t s, int border_rows)
+static int g_panel_fuse = 0;           // 0 auto, 1 never, 2 whenever the default panel kernels are selected
+void set_panel_fuse(int mode) { g_panel_fuse = mode; }
+
+// One launch per block column for factor + solve pays when many small matrices are in flight: a CTA then owns a matrix's
+// whole block column (35 us of latency-bound factor steps, then 64 rows of solve at a time), and co-resident CTAs drift
+// into different phases.  With few or large matrices the solve needs many CTAs per matrix: separate launches.
+int potrf_fuse_auto(int n, int B, int border_rows)
 {
+    if (!lite_panels() || g_potf2_mode != 0 || g_panel_fuse == 1) return 0;
+    if (g_panel_fuse == 2) return 1;
+    return (B >= 4 * sm_count() && n + border_rows <= 1664) ? 1 : 0;
+}
+
+int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
+                   int zero_upper_flag, cudaStream_t s, int border_rows, int fuse)
+{
+    if (fuse && (!lite_panels() || g_potf2_mode != 0)) { set_error("potrf_sequence: fused panels need the default panel kernels"); return GPMC_EINVAL; }
     if (border_rows < 0) { set_error("potrf_sequence: border_rows < 0"); return GPMC_EINVAL; }
     const int nr = n + border_rows;                     // rows that take part in the panel solves
     // ONE border row is carried by the idle diagonal warp of the update kernel (border duty); several of them (the
@@ -242,7 +256,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
     LookAhead *la = nullptr;
-    if (n > 2 * NB && (g_lookahead_mode == 2 || (g_lookahead_mode == 0 && 2 * B <= sm_count()))) la = lookahead_ctx();
+    if (!fuse && n > 2 * NB && (g_lookahead_mode == 2 || (g_lookahead_mode == 0 && 2 * B <= sm_count()))) la = lookahead_ctx();
     // streams: trailing updates / in-window updates / panel kernels
     const cudaStream_t sG = s;
     const cudaStream_t sQ = la ? (window > 0 ? la->inwin : s) : s;
@@ -304,6 +318,11 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 }
                 GPMC_CUDA_CHECK(cudaEventRecord(la->ev_q, sQ));
                 GPMC_CUDA_CHECK(cudaStreamWaitEvent(sP, la->ev_q, 0));
+            }
+            if (fuse) {
+                if ((rc = launch_panel_fused(A, n, nr, j0, Wj, strideW, info, zero_upper_flag, B, sP))) return rc;
+                if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
+                continue;
             }
             rc = !lite ? launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
                  : (g_potf2_mode == 2 ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
@@ -376,9 +395,14 @@ int border_get(BatchView A, int n, double *z, int ldv, const int *info, int B, c
     return 0;
 }
 
-int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s)
+int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cudaStream_t s, int solved)
 {
     if (B <= 0) return 0;
+    if (solved) {
+        // the fused panel launches solved the border row through the last block column as well
+        if (A.stride > 0x7fffffffLL) { set_error("border_finish: item stride %lld does not fit the vector stride", A.stride); return GPMC_EINVAL; }
+        return loglik ? launch_quad_logdet(A, n, A.base + (size_t)n * A.ld, (int)A.stride, loglik, info, B, s) : 0;
+    }
     if (A.stride > 0x7fffffffLL) { set_error("border_finish: item stride %lld does not fit the vector stride", A.stride); return GPMC_EINVAL; }
     const int j0 = (n - 1) / NB * NB;                   // last block column: its part of the row is updated, not solved
     const int nv = n - j0;

@@ -236,7 +236,7 @@ static int aux_form_R(const AuxCtx &c, BatchView V1, BatchView V2, int nitems, b
 
 // From a factored K+S (V1: L in the lower triangle, z in the border row up to its last block) to C = chol(R + 1e-11 I)
 // in V2, for the items of the views:
-static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitems)
+static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitems, int fuse1)
 {
     SweepBuffers &w = *c.w;
     cudaStream_t s = c.s;
@@ -248,7 +248,7 @@ static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitem
         if ((rc = aux_form_R(c, V1, V2, nitems, true))) return rc;
     } else {
         // ---- z = L^-1 g and the log marginal (:147)
-        if ((rc = border_finish(V1, w.n, w.G, w.info1, nitems, s))) return rc;
+        if ((rc = border_finish(V1, w.n, w.G, w.info1, nitems, s, fuse1))) return rc;
         if ((rc = border_get(V1, w.n, w.z, w.ldv, w.info1, nitems, s))) return rc;
         // ---- U = L^-T, m = g - S U z (:204), R = S - S U U^T S + 1e-11 I (:197-198,205)
         if ((rc = inverse_sequence(V1, w.n, nitems, w.Wsave, strideW, s))) return rc;
@@ -257,7 +257,7 @@ static int aux_downstream(const AuxCtx &c, BatchView V1, BatchView V2, int nitem
     }
     // ---- C = chol(R + 1e-11 I) (jitchol, :205)
     if ((rc = fill_int_mapped(w.info2, 0, V1.map, V1.count, nitems, s))) return rc;
-    return potrf_sequence(V2, w.n, nitems, w.info2, w.Wtmp, NB * NB, 0, 0, s);
+    return potrf_sequence(V2, w.n, nitems, w.info2, w.Wtmp, NB * NB, 0, 0, s, 0, potrf_fuse_auto(w.n, nitems, 0));
 }
 
 // Evaluate the auxiliary model at w.theta for the chains listed in `active` (w.map/w.count hold the same list).
@@ -279,8 +279,9 @@ static int aux_queue(const AuxCtx &c, int na)
     //      z = L^-1 g comes out of the update GEMMs and panel solves
     if ((rc = fill_int_mapped(w.info1, 0, w.map, w.count, na, s))) return rc;
     if ((rc = aux_fill(c, A1, na, nullptr))) return rc;
-    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w)))) return rc;
-    return aux_downstream(c, A1, A2, na);
+    const int fuse1 = potrf_fuse_auto(w.n, na, aux_border_rows(w));
+    if ((rc = potrf_sequence(A1, w.n, na, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w), fuse1))) return rc;
+    return aux_downstream(c, A1, A2, na, fuse1);
 }
 
 static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
@@ -294,6 +295,8 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
     int rc;
     if ((rc = aux_queue(c, na))) return rc;
     if (c.jitter_policy != GPMC_JITTER_PYGPS) return 0;
+    const int fuse1 = potrf_fuse_auto(w.n, na, aux_border_rows(w));      // what aux_queue used: the retries below must leave the
+                                                                         // border row in the same state
 
     // ---- one synchronisation: status of both factorisations
     std::vector<int> info1(w.cap), info2(w.cap);
@@ -328,7 +331,7 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             BatchView F1{w.buf1, mat1, w.ld, w.fmap, cnt};
             if ((rc = fill_int_mapped(w.info1, 0, w.fmap, cnt, nf, s))) return rc;
             if ((rc = aux_fill(c, F1, nf, w.jit))) return rc;
-            if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w)))) return rc;
+            if ((rc = potrf_sequence(F1, w.n, nf, w.info1, w.Wsave, strideW, NB * NB, 0, s, aux_border_rows(w), fuse1))) return rc;
             std::vector<int> still, tmp;
             if ((rc = failed_items(c, w.info1, todo, still, tmp))) return rc;
             for (int id : todo) if (tmp[id] == 0) recovered.push_back(id);
@@ -345,7 +348,7 @@ static int aux_eval(const AuxCtx &c, const std::vector<int> &active)
             GPMC_CUDA_CHECK(cudaMemcpyAsync(cnt, &nr, 4, cudaMemcpyHostToDevice, s));
             BatchView F1{w.buf1, mat1, w.ld, w.fmap, cnt};
             BatchView F2{w.buf2, mat, w.ld, w.fmap, cnt};
-            if ((rc = aux_downstream(c, F1, F2, nr))) return rc;
+            if ((rc = aux_downstream(c, F1, F2, nr, fuse1))) return rc;
             std::vector<int> bad2, tmp;
             if ((rc = failed_items(c, w.info2, recovered, bad2, tmp))) return rc;
             failed2.insert(failed2.end(), bad2.begin(), bad2.end());

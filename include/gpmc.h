@@ -241,7 +241,9 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  * key 8: form of the posterior covariance inside gpmc_sds_sweep / gpmc_sds_run: 0 = reduced, R = S - S (K+S)^-1 S (4/3 N^3
  *        flop per evaluation; default), 1 = literal, V = solve(L, K), R = K - V^T V, m = (R inv(S)) g exactly as
  *        sliceSample.py:197-198,204 write it (8/3 N^3; twice the workspace per chain -- query gpmc_sds_workspace_bytes
- *        after setting it).  Used for parity with the reference, not for speed. */
+ *        after setting it).  Used for parity with the reference, not for speed.
+ * key 9: panel factor + panel solve of a block column in ONE launch (one CTA per matrix): 0 = auto (many small matrices in
+ *        flight), 1 = never, 2 = whenever the default panel kernels are selected. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:

@@ -458,3 +458,61 @@ def test_odd_and_unaligned_sizes_through_the_fused_unit(gp, so):
         for b in range(2):
             ref = so.loglik_unit(x, G[b], H[b], form='chol')
             assert abs(ll[b] - ref) <= RTOL_LOGLIK * abs(ref), (n, b)
+
+
+@pytest.mark.parametrize('n', [64, 127, 128, 129, 200, 257, 385, 512, 641, 1000])
+def test_fused_panel_launches_agree_with_separate_ones(gp, so, n):
+    """gpmc_set_tuning(9, .): panel factor + panel solve of a block column in one launch (one CTA per matrix, chosen
+    automatically for many small matrices) against the separate potf2 / trsm launches.  The factor is the same arithmetic
+    in the same order -> bit-identical L; the log marginal differs only in how the border row's LAST block is solved
+    (panel-solve chain vs substitution kernel) -> 1e-13, and both match the oracle to 1e-10."""
+    import torch
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    H = np.array([[1., 10., 1.2], [5., 4., 2.5], [0.35, 2., 0.2], [2., 3., 0.5], [7.0, 6.0, 1.0]])
+    G = np.random.RandomState(n).standard_normal((5, n)) * H[:, 2:3]
+    A0 = gp.ops.cov_assemble(x, H, add_S=True)
+    out = {}
+    try:
+        for mode in (1, 2):
+            gp.ops.set_tuning(9, mode)
+            A = A0.clone()
+            info = gp.ops.potrf_batched(A, n=n, jitter_policy=gp.JITTER_NONE).cpu().numpy()
+            ll, info2 = gp.ops.loglik_host(x, G, H)
+            out[mode] = (A.cpu().numpy()[:, :, :n], info, ll, info2)
+    finally:
+        gp.ops.set_tuning(9, 0)
+    assert np.all(out[1][1] == 0) and np.all(out[2][1] == 0) and np.all(out[2][3] == 0)
+    assert np.array_equal(out[1][0], out[2][0])
+    np.testing.assert_allclose(out[2][2], out[1][2], rtol=1e-13)
+    for b in range(5):
+        ref = so.loglik_unit(x, G[b], H[b], form='chol')
+        assert abs(out[2][2][b] - ref) <= RTOL_LOGLIK * abs(ref)
+
+
+def test_fused_panel_launches_in_the_sds_sweep(gp):
+    """The same switch inside the sampler (bordered chol(K+S), chol(R + 1e-11 I), and the literal form's n more border
+    rows): theta', trips and log N(g) exact against the separate-launch path, f' within its resolution."""
+    import torch
+    from gpmc_b200 import ops
+    n, B = 200, 7
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    res = {}
+    try:
+        for lit in (0, 1):
+            ops.set_tuning(8, lit)
+            for mode in (1, 2):
+                ops.set_tuning(9, mode)
+                F = torch.tensor(F0.copy()).cuda(); H = torch.tensor(H0.copy()).cuda()
+                nt, ll, st = ops.sds_sweep(x, y, F, H, scale, 600, seed=3, workspace=ops.Workspace())
+                res[(lit, mode)] = (F.cpu().numpy(), H.cpu().numpy(), nt.cpu().numpy(), ll.cpu().numpy(), st.cpu().numpy())
+    finally:
+        ops.set_tuning(9, 0); ops.set_tuning(8, 0)
+    for lit in (0, 1):
+        a, b = res[(lit, 1)], res[(lit, 2)]
+        assert np.all(a[4] == 0) and np.all(b[4] == 0)
+        assert np.array_equal(a[2], b[2])
+        np.testing.assert_allclose(b[1], a[1], rtol=1e-12)
+        np.testing.assert_allclose(b[3], a[3], rtol=1e-10)
+        assert np.abs(a[0] - b[0]).max() < 5e-2

@@ -51,9 +51,30 @@ def main():
     ap.add_argument('--panel', type=int, default=128)
     ap.add_argument('--tag', default='r02')
     ap.add_argument('--no-json', action='store_true')
+    ap.add_argument('--how', default='ncu --set full --clock-control none')
     args = ap.parse_args()
-    out = subprocess.run(['ncu', '-i', args.rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    if args.rep.endswith('.ncu-rep'):
+        out = subprocess.run(['ncu', '-i', args.rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    else:
+        out = open(args.rep).read()
+    rows = [r for r in csv.reader(out.splitlines()) if r]
+    while rows and rows[0][0] != 'ID':           # ncu log files start with ==PROF== lines
+        rows.pop(0)
+    if 'Metric Name' in rows[0]:
+        # long format of `ncu --metrics ... --csv --log-file`: one row per (launch, metric) -> pivot to the wide format
+        h = rows[0]
+        iid, ik, imn, imu, imv = h.index('ID'), h.index('Kernel Name'), h.index('Metric Name'), h.index('Metric Unit'), h.index('Metric Value')
+        names, unit_of, per_id, kname = [], {}, collections.OrderedDict(), {}
+        for r in rows[1:]:
+            if len(r) <= imv:
+                continue
+            if r[imn] not in unit_of:
+                names.append(r[imn]); unit_of[r[imn]] = r[imu]
+            per_id.setdefault(r[iid], {})[r[imn]] = r[imv]
+            kname[r[iid]] = r[ik]
+        hdr = ['ID', 'Kernel Name'] + names
+        units = ['', ''] + [unit_of[n] for n in names]
+        rows = [hdr, units] + [[i, kname[i]] + [d.get(n, 'nan') for n in names] for i, d in per_id.items()]
     hdr, units = rows[0], rows[1]
     ni = hdr.index('Kernel Name')
     ix = {k: hdr.index(v) for k, v in COLS.items() if v in hdr}
@@ -84,8 +105,8 @@ def main():
         tw = sum(w for _, w in pairs)
         return sum(p * w for p, w in pairs) / tw if tw > 0 else float('nan')
 
-    lines = ['ncu --set full --clock-control none, one log-lik pass, N=%d, %d matrices (tools/ncu_workload.py); per kernel: launches, '
-             'summed duration, DRAM bytes read/written, achieved DRAM GB/s over the summed duration, duration-weighted pipe figures' % (args.nobs, args.chains),
+    lines = ['%s, one log-lik pass, N=%d, %d matrices (tools/ncu_workload.py); per kernel: launches, '
+             'summed duration, DRAM bytes read/written, achieved DRAM GB/s over the summed duration, duration-weighted pipe figures' % (args.how, args.nobs, args.chains),
              '%-44s %5s %10s %12s %12s %9s %8s %8s %8s %8s %5s' % ('kernel', 'n', 'total_us', 'dram_rd_MB', 'dram_wr_MB', 'dram_GB/s', 'dram%', 'dmma%', 'fp64%', 'issue%', 'regs')]
     for name, a in agg.items():
         gbs = (a['rd'] + a['wr']) / a['dur'] / 1e9 if a['dur'] > 0 else float('nan')
@@ -96,10 +117,10 @@ def main():
     open(os.path.join(ROOT, 'profiles', '%s_ncu_kernels.txt' % args.tag), 'w').write(text + '\n')
     if args.no_json:
         return
-    upd = [a for name, a in agg.items() if name.startswith('gemm_dmma_tma_kernel')]
-    asm = [a for name, a in agg.items() if name.startswith('cov_assemble_kernel')]
-    d = {'source': 'profiles/%s_ncu_kernels.txt (ncu --set full of tools/ncu_workload.py --nobs %d --chains %d; '
-                   'dram__bytes_read.sum + dram__bytes_write.sum over all update launches of one pass / chains)' % (args.tag, args.nobs, args.chains),
+    upd = [a for name, a in agg.items() if 'gemm_dmma_tma_kernel' in name]
+    asm = [a for name, a in agg.items() if 'cov_assemble_kernel' in name]
+    d = {'source': 'profiles/%s_ncu_kernels.txt (%s of tools/ncu_workload.py --nobs %d --chains %d; '
+                   'dram__bytes_read.sum + dram__bytes_write.sum over all update launches of one pass / chains)' % (args.tag, args.how, args.nobs, args.chains),
          'update_kernel': [], 'assemble_kernel': []}
     path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.isfile(path):
