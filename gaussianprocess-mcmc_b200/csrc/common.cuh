@@ -122,13 +122,20 @@ int launch_potf2_lite(BatchView A, int n, int j0, double *W, long long strideW, 
 // factored in 16 steps of 8 columns (the default panel factor kernel)
 int launch_potf2_reg(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
                      int B, cudaStream_t s);
+// potf2_flow.cu : the register-resident panel factor kernel as a dataflow program (flags in shared memory instead of block
+// barriers between the 16 steps; measured slower than potf2_reg.cu, kept for A/B: gpmc_set_tuning(1, 3)), and its fused form
+int launch_potf2_flow(BatchView A, int n, int j0, double *W, long long strideW, int *info, int zero_upper,
+                      int B, cudaStream_t s);
+int launch_panel_fused_flow(BatchView A, int n, int n_rows, int j0, double *W, long long strideW, int *info, int zero_upper,
+                            int B, cudaStream_t s);
 // potf2_reg.cu : panel factor AND panel solve of block column j0 in one launch (n_rows = n + border rows; in the last block
 // column the border rows are solved too) -- for many small matrices in flight
 int launch_panel_fused(BatchView A, int n, int n_rows, int j0, double *W, long long strideW, int *info, int zero_upper,
                        int B, cudaStream_t s);
 void set_lookahead_mode(int mode); // potrf_sequence: 0 auto (few matrices in flight), 1 off, 2 on
 void set_potrf_window(int w);      // override the window of the windowed schedule (multiple of NB; 0 = default)
-void set_potf2_mode(int mode);     // 0: register-resident kernel (default), 2: the shared-memory lite kernel, 1: always the full-inverse one
+void set_potf2_mode(int mode);     // 0: register-resident kernel (default), 3: the same as a dataflow program (no block barriers),
+                                   // 2: the shared-memory lite kernel, 1: always the full-inverse one
 
 // trsm_panel.cu : rows below the factored diagonal block at (j0, j0):  X L11^T = A21  (W = L11^-1 from launch_potf2)
 int launch_trsm_panel(BatchView A, int n, int j0, const double *W, long long strideW, int B, cudaStream_t s);

@@ -25,7 +25,9 @@ constexpr int ASM_TPC = 1;      // tiles per CTA (4 was measured: N=4096 x 256 4
 // DT == 0: generic D.  The kernel is instruction-issue bound (ncu: 79 % issue slots, FP64 pipe 47 %, DRAM 33 %), so the
 // fast path strips everything that is not the exp itself: no bounds tests on interior tiles, no diagonal tests off
 // the diagonal.
-template <int DT>
+// PRED: the K / sn^2 + I variant of inf_mcmc (GPMC_ASM_PRED) -- a template parameter, not a run-time test: a uniform
+// `if (pred)` in the fast path cost the hot (non-PRED) instantiation 20 % (3.5 vs 4.2 TB/s at N=4096, round 2).
+template <int DT, bool PRED>
 __global__ void __launch_bounds__(256)
 cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *__restrict__ hyp, int P, int n_ell,
                     int flags, const double *__restrict__ jitter, BatchView A)
@@ -59,7 +61,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
         s_scal[0] = sf2;
         s_scal[1] = (flags & GPMC_ASM_ADD_S) ? Sii : 0.0;
         s_scal[2] = jitter ? jitter[m] : 0.0;
-        if (flags & GPMC_ASM_PRED) {
+        if (PRED) {
             // inf_mcmc (sliceSample.py:256-257): sn2 = likfunc.sn**2 with likfunc.sn = exp(log_sigma); K/sn2 + eye(n)
             const double snl = exp(log(sn));
             s_scal[3] = snl * snl;
@@ -70,7 +72,7 @@ cov_assemble_kernel(const double *__restrict__ x, int N, int Drt, const double *
     const int warp = tid >> 5, lane = tid & 31;
     const double sf2 = s_scal[0];
     const double diag_add = s_scal[1], jit = s_scal[2], sn2 = s_scal[3];
-    const bool pred = (flags & GPMC_ASM_PRED) != 0;
+    constexpr bool pred = PRED;
     const bool has_jit = (jitter != nullptr);
     double *Ab = A.base + (size_t)m * A.stride;
     const int cl = 2 * lane;
@@ -180,13 +182,19 @@ int launch_cov_assemble(const double *x, int N, int D, const double *hyp, int P,
     const int nt = (N + AT - 1) / AT;
     dim3 grid((nt * (nt + 1) / 2 + ASM_TPC - 1) / ASM_TPC, B);
     prof_begin(KC_ASSEMBLE, s);
+#define GPMC_ASM_LAUNCH(DT_)                                                                                                     \
+    do {                                                                                                                          \
+        if (flags & GPMC_ASM_PRED) cov_assemble_kernel<DT_, true><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A);  \
+        else cov_assemble_kernel<DT_, false><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A);                       \
+    } while (0)
     switch (D) {
-        case 1: cov_assemble_kernel<1><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;
-        case 2: cov_assemble_kernel<2><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;
-        case 3: cov_assemble_kernel<3><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;
-        case 4: cov_assemble_kernel<4><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;
-        default: cov_assemble_kernel<0><<<grid, 256, 0, s>>>(x, N, D, hyp, P, n_ell, flags, jitter, A); break;
+        case 1: GPMC_ASM_LAUNCH(1); break;
+        case 2: GPMC_ASM_LAUNCH(2); break;
+        case 3: GPMC_ASM_LAUNCH(3); break;
+        case 4: GPMC_ASM_LAUNCH(4); break;
+        default: GPMC_ASM_LAUNCH(0); break;
     }
+#undef GPMC_ASM_LAUNCH
     prof_end(KC_ASSEMBLE, s);
     GPMC_LAUNCH_CHECK();
     return 0;

@@ -53,14 +53,22 @@ __device__ __forceinline__ void dmma884_r(double &c0, double &c1, double a, doub
 // a <= 0 or NaN gives NaN / inf, which is what a failed pivot is allowed to produce (info is set by the caller).
 __device__ __forceinline__ double pivot_rsqrt(double a)
 {
+    // one third-order step from the hardware approximation (MUFU.RSQ64H, ~2^-22):  e = 1/2 - (a/2) y^2,
+    // y <- y + y e (1 + 3/2 e)  (error ~ e^3): 4 dependent FP64 operations
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double h = 0.5 * a;
-    double e = fma(-(h * y), y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-(h * y), y, 0.5);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-(h * y), y, 0.5);
+    return fma(y * e, fma(1.5, e, 1.0), y);
+}
+// 1/a for the pivot CHAIN (the next pivot is a_{c+1,c+1} - a_{c+1,c}^2 / a_cc and must not wait for the square root):
+// MUFU.RCP64H + one third-order step,  e = 1 - a y,  y <- y + y (e + e^2): 3 dependent FP64 operations
+__device__ __forceinline__ double pivot_rcp(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 
 // slot -> (block row, block column) of warp w (see the header comment)
@@ -172,18 +180,19 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (!(piv > 0.0) && fail == 0) fail = j0 + b * 8 + c + 1;           // dpotf2: ajj <= 0 or NaN
+                // the next pivot first (it is the critical path of the whole kernel): row c+1 holds its diagonal entry and
+                // its own unscaled multiplier a_{c+1,c}, so  a_{c+1,c+1} - a_{c+1,c}^2 / a_cc  needs the reciprocal of the pivot
+                // only -- the reciprocal square root (one dependent operation longer) is off the chain
+                const double pr = pivot_rcp(piv);
                 const double rinv = pivot_rsqrt(piv);
-                v[c] = v[c] * rinv;                                                 // lane c: piv * rinv = sqrt(piv)
-                if (c < 7) {
-                    // the next pivot first: row c+1 holds both its diagonal entry and its own multiplier l_{c+1,c}, so
-                    // the value needs no shuffle before it is broadcast
-                    piv = __shfl_sync(0xffffffffu, fma(-v[c], v[c], v[c + 1]), c + 1);
-                }
+                const double pnext = (c < 7) ? __shfl_sync(0xffffffffu, fma(-(v[c] * v[c]), pr, v[c + 1]), c + 1) : 0.0;
+                v[c] = (l16 == c) ? piv * rinv : v[c] * rinv;                       // the pivot row: sqrt(piv) from the pivot the chain used
 #pragma unroll
                 for (int j = c + 1; j < 8; ++j) {
                     const double ljc = __shfl_sync(0xffffffffu, v[c], j);           // l_{j,c} from row j of the fragment
                     v[j] = fma(-v[c], ljc, v[j]);
                 }
+                piv = pnext;
             }
             if (lane < 8) {
                 const int gr = b * 8 + r8;
@@ -258,6 +267,8 @@ potf2_reg_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long s
         // ------------------------------------------------------------------ C: fragments (r, c), c > b: a suffix of the slots
         {
             const int start = (b + 1 <= w) ? 2 * (b + 1) : w + b + 2;
+            // (walking the suffix twice, k-step 0 of every slot first, and picking phase B's fragments before the barrier were
+            //  both measured: 34.8 -> 36.2 us per block -- not kept)
             switch (start) {
                 PR_CASE(0) PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7) PR_CASE(8)
                 PR_CASE(9) PR_CASE(10) PR_CASE(11) PR_CASE(12) PR_CASE(13) PR_CASE(14) PR_CASE(15) PR_CASE(16)

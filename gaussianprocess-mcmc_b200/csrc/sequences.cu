@@ -163,23 +163,6 @@ int copy_rows(double *dst, int ldd, const double *src, int lds, int n, int rows,
 // matrices: B * N/128 < 1024, e.g. the single N=16384 matrix of BASELINE config 4) the columns are grouped in WINDOWS:
 // left-looking inside a window (contraction limited to the window), then ONE right-looking trailing update
 // A22 -= L21 L21^T with thousands of tiles and K = window -- the classic DMMA trailing update.
-static int g_window_override = 0;
-void set_potrf_window(int w) { g_window_override = (w > 0 && w % NB == 0) ? w : 0; }
-
-static int potrf_window_for(int n, int B)
-{
-    const int nt = (n + 127) / 128;                 // 128-row tiles of a block column
-    if (g_window_override) return g_window_override >= n ? 0 : g_window_override;   // experiments: forced (>= n: plain left-looking)
-    if ((long long)B * nt >= 1024) return 0;
-    return n >= 8192 ? 1024 : 512;
-}
-
-static int g_trsm_mode = 0;
-void set_trsm_mode(int mode) { g_trsm_mode = mode; }
-static int g_potf2_mode = 0;
-void set_potf2_mode(int mode) { g_potf2_mode = mode; }
-static bool lite_panels() { return g_trsm_mode == 0 && g_potf2_mode != 1; }
-
 static int sm_count()
 {
     static int sms = 0;
@@ -190,6 +173,26 @@ static int sm_count()
     }
     return sms;
 }
+
+static int g_window_override = 0;
+void set_potrf_window(int w) { g_window_override = (w > 0 && w % NB == 0) ? w : 0; }
+
+static int potrf_window_for(int n, int B)
+{
+    const int nt = (n + 127) / 128;                 // 128-row tiles of a block column
+    if (g_window_override) return g_window_override >= n ? 0 : g_window_override;   // experiments: forced (>= n: plain left-looking)
+    // plain left-looking once the launches fill the chip several times over -- unless the look-ahead schedule is on anyway
+    // (at most #SMs/2 matrices): there windows of 512 measured 3.5 % faster than none at N=2048 x 64 (tools/window_c2.py)
+    if ((long long)B * nt >= 1024 && 2 * B > sm_count()) return 0;
+    return n >= 8192 ? 1024 : 512;
+}
+
+static int g_trsm_mode = 0;
+void set_trsm_mode(int mode) { g_trsm_mode = mode; }
+static int g_potf2_mode = 0;
+void set_potf2_mode(int mode) { g_potf2_mode = mode; }
+static bool lite_panels() { return g_trsm_mode == 0 && g_potf2_mode != 1; }
+
 
 // Look-ahead.  With few matrices in flight the panel kernels (one CTA per matrix) leave most of the chip idle, so the
 // sequence is spread over up to three streams:
@@ -232,15 +235,18 @@ void set_panel_fuse(int mode) { g_panel_fuse = mode; }
 // into different phases.  With few or large matrices the solve needs many CTAs per matrix: separate launches.
 int potrf_fuse_auto(int n, int B, int border_rows)
 {
-    if (!lite_panels() || g_potf2_mode != 0 || g_panel_fuse == 1) return 0;
+    if (!lite_panels() || (g_potf2_mode != 0 && g_potf2_mode != 3) || g_panel_fuse == 1) return 0;
     if (g_panel_fuse == 2) return 1;
+    // many small matrices (co-resident CTAs drift into different phases), or any number of very small ones (two launches
+    // and the last-block solve of the border row saved per block column: latency of a single small chain)
+    if (n + border_rows <= 640) return 1;
     return (B >= 4 * sm_count() && n + border_rows <= 1664) ? 1 : 0;
 }
 
 int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long strideW, long long w_step,
                    int zero_upper_flag, cudaStream_t s, int border_rows, int fuse)
 {
-    if (fuse && (!lite_panels() || g_potf2_mode != 0)) { set_error("potrf_sequence: fused panels need the default panel kernels"); return GPMC_EINVAL; }
+    if (fuse && (!lite_panels() || (g_potf2_mode != 0 && g_potf2_mode != 3))) { set_error("potrf_sequence: fused panels need the default panel kernels"); return GPMC_EINVAL; }
     if (border_rows < 0) { set_error("potrf_sequence: border_rows < 0"); return GPMC_EINVAL; }
     const int nr = n + border_rows;                     // rows that take part in the panel solves
     // ONE border row is carried by the idle diagonal warp of the update kernel (border duty); several of them (the
@@ -320,13 +326,15 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 GPMC_CUDA_CHECK(cudaStreamWaitEvent(sP, la->ev_q, 0));
             }
             if (fuse) {
-                if ((rc = launch_panel_fused(A, n, nr, j0, Wj, strideW, info, zero_upper_flag, B, sP))) return rc;
+                if ((rc = (g_potf2_mode == 3 ? launch_panel_fused_flow(A, n, nr, j0, Wj, strideW, info, zero_upper_flag, B, sP)
+                                             : launch_panel_fused(A, n, nr, j0, Wj, strideW, info, zero_upper_flag, B, sP)))) return rc;
                 if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sP));
                 continue;
             }
             rc = !lite ? launch_potf2(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
                  : (g_potf2_mode == 2 ? launch_potf2_lite(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
-                                      : launch_potf2_reg(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP));
+                    : (g_potf2_mode == 3 ? launch_potf2_flow(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)
+                                         : launch_potf2_reg(A, n, j0, Wj, strideW, info, zero_upper_flag, B, sP)));
             if (rc) return rc;
             if (j0 + NB < n && (rc = (g_trsm_mode == 1 ? launch_trsm_panel(A, nr, j0, Wj, strideW, B, sP)
                                                         : launch_trsm_panel8(A, nr, j0, Wj, strideW, B, sP)))) return rc;

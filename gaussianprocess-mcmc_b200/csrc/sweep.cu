@@ -510,7 +510,9 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
     // run-ahead: deep enough that the device never waits for the host, shallow enough that the idle rounds queued past the
     // end cost little next to a round of real work
     const double round_flops = (double)std::min(cap, B) * (4.0 / 3.0) * (double)N * N * N;
-    int runahead = g_sds_runahead > 0 ? g_sds_runahead : (round_flops > 2e11 ? 4 : (round_flops > 2e9 ? 3 : 2));
+    // (a single small chain: a round is ~60 launches of a few microseconds each, an idle round costs as much as a real one,
+    //  so the host waits for every status word there -- run-ahead 1)
+    int runahead = g_sds_runahead > 0 ? g_sds_runahead : (round_flops > 2e11 ? 4 : (round_flops > 2e10 ? 3 : (round_flops > 1e9 ? 2 : 1)));
     runahead = std::min(runahead, ResidentHost::RING - 1);
     g_sds_rounds = g_sds_idle_rounds = g_sds_ladders = 0;
 

@@ -228,8 +228,9 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
 
 /* Kernel tuning knobs for experiments.
  * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default).
- * key 1: panel factor kernel (0 = the register-resident kernel potf2_reg.cu (default), 2 = the shared-memory kernel
- *        potf2_lite.cu -- both emit the 8x8 diagonal inverses only --, 1 = always the full-inverse kernel potf2.cu).
+ * key 1: panel factor kernel (0 = the register-resident kernel potf2_reg.cu (default), 3 = the same fragments as a dataflow
+ *        program without block barriers, potf2_flow.cu, 2 = the shared-memory kernel potf2_lite.cu -- all three emit the
+ *        8x8 diagonal inverses only --, 1 = always the full-inverse kernel potf2.cu).
  * key 2: look-ahead in the blocked Cholesky (panel kernels overlapped with the update GEMM on side streams):
  *        0 auto (on when at most #SMs/2 matrices are in flight), 1 off, 2 on.
  * key 3: window (columns, multiple of 128) of the windowed schedule used for few large matrices; 0 = default.

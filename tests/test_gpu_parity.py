@@ -130,9 +130,9 @@ def test_potrf_reports_lapack_info(gp):
 
 @pytest.mark.parametrize('n', [37, 128, 300, 1000])
 def test_both_panel_factor_kernels_agree(gp, so, n):
-    """potf2_reg.cu (register-resident fragments, default = mode 0), potf2.cu (full block inverse, mode 1) and
-    potf2_lite.cu (shared-memory block, diagonal sub-block inverses, mode 2): force each in turn over the same matrices,
-    incl. a non-PD one (LAPACK info must match)."""
+    """potf2_reg.cu (register-resident fragments, default = mode 0), potf2_flow.cu (the same as a dataflow program without
+    block barriers, mode 3; must be BIT-identical to mode 0), potf2.cu (full block inverse, mode 1) and potf2_lite.cu
+    (shared-memory block, mode 2): force each in turn over the same matrices, incl. a non-PD one (LAPACK info must match)."""
     import torch
     import scipy.linalg
     x = np.arange(n, dtype=np.float64).reshape(n, 1)
@@ -141,7 +141,7 @@ def test_both_panel_factor_kernels_agree(gp, so, n):
     bad = min(n - 1, 170)
     out = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             gp.ops.set_tuning(1, mode)
             A = A0.clone()
             A[3, bad, bad] = -1.0
@@ -151,6 +151,7 @@ def test_both_panel_factor_kernels_agree(gp, so, n):
         gp.ops.set_tuning(1, 0)
     (L1, i1) = out[1]
     Ah = A0.cpu().numpy()[:, :, :n]
+    assert np.array_equal(out[0][0][:3], out[3][0][:3]) and np.array_equal(out[0][1], out[3][1])
     for mode in (0, 2):
         L2, i2 = out[mode]
         assert np.array_equal(i1, i2) and np.all(i1[:3] == 0) and i1[3] == bad + 1
@@ -473,14 +474,16 @@ def test_fused_panel_launches_agree_with_separate_ones(gp, so, n):
     A0 = gp.ops.cov_assemble(x, H, add_S=True)
     out = {}
     try:
-        for mode in (1, 2):
-            gp.ops.set_tuning(9, mode)
+        for mode in (1, 2, 3):
+            gp.ops.set_tuning(9, min(mode, 2))
+            gp.ops.set_tuning(1, 3 if mode == 3 else 0)          # mode 3: fused launches of the dataflow kernel
             A = A0.clone()
             info = gp.ops.potrf_batched(A, n=n, jitter_policy=gp.JITTER_NONE).cpu().numpy()
             ll, info2 = gp.ops.loglik_host(x, G, H)
             out[mode] = (A.cpu().numpy()[:, :, :n], info, ll, info2)
     finally:
-        gp.ops.set_tuning(9, 0)
+        gp.ops.set_tuning(9, 0); gp.ops.set_tuning(1, 0)
+    assert np.array_equal(out[3][0], out[2][0]) and np.array_equal(out[3][2], out[2][2])
     assert np.all(out[1][1] == 0) and np.all(out[2][1] == 0) and np.all(out[2][3] == 0)
     assert np.array_equal(out[1][0], out[2][0])
     np.testing.assert_allclose(out[2][2], out[1][2], rtol=1e-13)
