@@ -389,6 +389,58 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     return rec
 
 
+def sub_c1(gp, np, iters=30, cpu_iters=6, literal=False):
+    """BASELINE config 1 (demoRegression.py: N=200, one chain): the reference's caller loop (demoRegression.py:23-30) on
+    the drop-in `kcMCMC.sliceSample.surrogate_slice_sampling`, host arrays in / out, global numpy stream seeded like the
+    reference (seed 124, hyp0 = [0.35, 2.0, 0.2]); the CPU oracle consumes the same stream beside it."""
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    n = 200
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array([10., 10., 5.])
+    sds = gp.kcMCMC.sliceSample
+    if literal:
+        gp.ops.set_tuning(8, 1)
+    try:
+        np.random.seed(124)
+        f, h = np.zeros(n), np.array([0.35, 2.0, 0.2])
+        sds.surrogate_slice_sampling(f, x, y, h, scale, iter=0)             # warm-up
+        np.random.seed(124)
+        gh = []
+        t0 = time.perf_counter()
+        for i in range(iters):
+            f, h = sds.surrogate_slice_sampling(f, x, y, h, scale, iter=i)
+            gh.append(h.copy())
+        t_gpu = (time.perf_counter() - t0) / iters
+    finally:
+        if literal:
+            gp.ops.set_tuning(8, 0)
+    rs = np.random.RandomState(124)
+    f, h = np.zeros(n), np.array([0.35, 2.0, 0.2])
+    oh, trips = [], []
+    t0 = time.perf_counter()
+    for i in range(cpu_iters):
+        z, v, u0 = rs.standard_normal(n), rs.random_sample(3), rs.random_sample()
+        st = rs.get_state()
+        U = rs.random_sample((256, 3))
+        tr = so.SweepTrace()
+        f, h = so.surrogate_slice_sampling(f, x, y, h, scale, i, Tape(z, v, u0, U), trace=tr)
+        rs.set_state(st)
+        rs.random_sample((tr.n_trips, 3))
+        oh.append(h.copy())
+        trips.append(tr.n_trips)
+    t_cpu = (time.perf_counter() - t0) / cpu_iters
+    gh, oh = np.array(gh), np.array(oh)
+    rel = np.abs(gh[:cpu_iters] - oh).max(axis=1) / np.abs(oh).max(axis=1)
+    same = int(np.argmax(rel > 1e-9)) if np.any(rel > 1e-9) else cpu_iters
+    return {'name': 'C1_chain' + ('_literalR' if literal else ''), 'kind': 'drop_in_chain',
+            'workload': 'BASELINE config 1 (demoRegression.py): N=200, one chain, surrogate_slice_sampling called like '
+                        'demoRegression.py:25, numpy arrays in and out, global numpy stream',
+            'n': n, 'iterations': iters, 'ms_per_iteration': 1e3 * t_gpu, 'cpu_oracle_ms_per_iteration': 1e3 * t_cpu,
+            'cpu_oracle_iterations': cpu_iters, 'mean_trips_cpu': float(np.mean(trips)),
+            'iterations_with_identical_theta_to_1e-9': same, 'posterior_form': 'literal' if literal else 'reduced'}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -494,6 +546,8 @@ def run_b200(args):
             return want is None or name in want
         try:
             if world == 1:
+                if on('C1_chain'):
+                    configs.append(sub_c1(gp, np))
                 if on('C2_loglik'):
                     configs.append(sub_loglik(gp, torch, np, 'C2_loglik', 2048, 64, 0, 10, peak_tf, 8,
                                               'BASELINE config 2: IH45-shaped series, N=2048, SE+noise, 64 chains, 1 B200'))

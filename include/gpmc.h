@@ -28,9 +28,13 @@
  *  - threading: like the reference (one Python thread, sliceSample.py uses the
  *    global numpy RNG) the library is meant for ONE host thread per process and
  *    one process per GPU; it keeps per-process state (side streams and events of
- *    the look-ahead schedule, the host-path staging buffers, the last-error text)
- *    and is not re-entrant.  Calls are asynchronous on `stream` except where a
- *    jitter policy needs info[] on the host (one synchronisation per wave).
+ *    the look-ahead schedule, the host-path staging buffers, the pinned status
+ *    ring of the resident sampler loop -- one per device --, the last-error text)
+ *    and is not re-entrant.  Kernel attributes are set per device, so one thread
+ *    may drive several devices in turn.  Calls are asynchronous on `stream`
+ *    except where a jitter policy needs info[] on the host (one synchronisation
+ *    per wave) and inside gpmc_sds_sweep / gpmc_sds_run, which return when the
+ *    last chain has finished (the host polls a status word meanwhile).
  */
 #ifndef GPMC_H
 #define GPMC_H
