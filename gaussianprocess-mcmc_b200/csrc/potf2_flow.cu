@@ -1,22 +1,21 @@
-// Panel factor kernel, fourth form: potf2_reg.cu's register-resident fragments, but the 16 factor steps are no longer
-// separated by block barriers -- the warps run a DATAFLOW program synchronised by flags in shared memory.
+// Panel factor kernel, fourth form: potf2_reg.cu's register-resident fragments, with the single-warp factor step taken off
+// the other warps' critical path by SPLIT named barriers (bar.arrive / bar.sync) instead of two block barriers per step.
 //
 // In potf2_reg.cu every step is  A (one warp factors the 8x8 diagonal fragment) | barrier | B (all warps solve their
-// fragments of the block column) | barrier | C (all warps update their live fragments), so the critical path of a step is
-// A + the slowest warp's B + the slowest warp's C + two barriers (ncu r02f: 66 k cycles per block, of which the pivot chain
-// itself -- 128 x {broadcast, rsqrt, scale, update} -- is under a quarter).  The true dependency chain is much shorter:
+// fragments of the block column) | barrier | C (all warps update their live fragments); phase A alone is 49 % of the wall
+// time (ncu, profiles/r02k) and nothing overlaps it.  The true dependency chain is much shorter:
 //     A(b)  ->  solve of ONE fragment, (b+1, b)  ->  update of ONE fragment, (b+1, b+1)  ->  A(b+1)
-// Here the warp that owns block row b+1 does exactly that and nothing else before it factors, while the other warps (and
-// the same warp afterwards) work through the remaining solves and updates in the shadow of the next factor step:
-//   * every solved fragment X(r, c) is written ONCE to its own place in shared memory (the lower 8x8 blocks of L11, 68 KB --
-//     the layout the fused panel solve needs anyway), so there are no write-after-read hazards and consumers may lag;
-//   * flag f_lw = last block column whose diagonal factor (L8, W8) is published; flag f_x[r] = last block column whose
-//     fragment of block row r is published; writers: data stores, __syncwarp, st.release by one lane; readers: ld.acquire
-//     by every lane, spinning (warps of a CTA make independent forward progress);
-//   * phase C's suffix jump and phase B's 17-way pick are those of potf2_reg.cu; each consumed X(c, b) waits for f_x[c] >= b.
-// Every wait is on something an earlier step (or an earlier phase of the same step) produces, so the program cannot
-// deadlock: by induction over (step, phase).  Results are bit-identical to potf2_reg.cu (same operations on the same
-// operands, only their interleaving changes).
+// Here the warp that owns block row b+1 does exactly that and nothing else before it factors; the other seven warps run
+// their solves and updates of step b meanwhile.  Synchronisation per step (barrier ids alternate with the parity of b):
+//     P_b  "L8 / W8 of step b are published"      owner(b): bar.arrive      the other warps: bar.sync
+//     X_b  "every X(r, b) is published"           owner(b+1): bar.arrive    the other warps: bar.sync
+//     Q_b  "... and visible to owner(b+1)"        the other warps: bar.arrive (right after X_b)   owner(b+1): bar.sync,
+//                                                  after it has factored -- by then the others are long past it
+// Every solved fragment X(r, c) and every L8 / W8 is written ONCE to its own place in shared memory (the lower 8x8 blocks
+// of L11, 76 KB -- the layout the fused panel solve needs anyway), so there are no write-after-read hazards.  A first
+// version synchronised with flags in shared memory (st.release / spinning ld.acquire): 38.6 us per block against the
+// 34.8 us of potf2_reg.cu -- the fences and the spinning warps cost more than the barriers they replaced.
+// Results are bit-identical to potf2_reg.cu (same operations on the same operands, only their interleaving changes).
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
@@ -57,22 +56,13 @@ __device__ __forceinline__ double pivot_rcp_w(double a)
     return fma(y, fma(e, e, e), y);
 }
 
-__device__ __forceinline__ int flag_load(const int *p)
+__device__ __forceinline__ void bar_sync_n(int id)
 {
-    int v;
-    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];\n" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
+    asm volatile("barrier.sync %0, %1;\n" ::"r"(id), "r"(PW_THREADS) : "memory");
 }
-__device__ __forceinline__ void flag_store(int *p, int v)
+__device__ __forceinline__ void bar_arrive_n(int id)
 {
-    asm volatile("st.release.cta.shared.b32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-// bounded spin: a logic error must not hang the GPU
-__device__ __forceinline__ void flag_wait_ge(const int *p, int v)
-{
-    for (unsigned it = 0; it < (1u << 24); ++it)
-        if (flag_load(p) >= v) return;
-    __trap();
+    asm volatile("barrier.arrive %0, %1;\n" ::"r"(id), "r"(PW_THREADS) : "memory");
 }
 
 __device__ __forceinline__ void slot_rc_w(int s, int w, int &R, int &C, bool &isA)
@@ -82,10 +72,10 @@ __device__ __forceinline__ void slot_rc_w(int s, int w, int &R, int &C, bool &is
     R = isA ? w : PW_NF - 1 - w;
 }
 
-// phase C for one slot: acc -= X_R X_C^T with X_C = block (C, b) of the published factor (waits for it)
+// phase C for one slot: acc -= X_R X_C^T with X_C = block (C, b) of the published factor
 template <int S>
 __device__ __forceinline__ void slot_update_w(double (&acc)[PW_SLOTS][2], int w, int b, int skip, double xa0, double xa1, double xb0, double xb1,
-                                              const double *Lc, const int *f_x, int frag_off)
+                                              const double *Lc, int frag_off)
 {
     if (S == skip) return;
     int R, C; bool isA;
@@ -93,16 +83,13 @@ __device__ __forceinline__ void slot_update_w(double (&acc)[PW_SLOTS][2], int w,
     const double n0 = isA ? -xa0 : -xb0, n1 = isA ? -xa1 : -xb1;
     double2 xc;
     if (C == R) xc = make_double2(-n0, -n1);                              // diagonal fragment: X_C is this warp's own pair
-    else {
-        flag_wait_ge(&f_x[C], b);
-        xc = *reinterpret_cast<const double2 *>(&Lc[(C * (C + 1) / 2 + b) * 64 + frag_off]);
-    }
+    else xc = *reinterpret_cast<const double2 *>(&Lc[(C * (C + 1) / 2 + b) * 64 + frag_off]);
     dmma884_w(acc[S][0], acc[S][1], n0, xc.x);
     dmma884_w(acc[S][0], acc[S][1], n1, xc.y);
 }
 
-#define PW_CASE(S) case S: slot_update_w<S>(acc, w, b, skip, xa0, xa1, xb0, xb1, Lc, f_x, frag_off);
-#define PW_ONE(S) case S: slot_update_w<S>(acc, w, b, -1, xa0, xa1, xb0, xb1, Lc, f_x, frag_off); break;
+#define PW_CASE(S) case S: slot_update_w<S>(acc, w, b, skip, xa0, xa1, xb0, xb1, Lc, frag_off);
+#define PW_ONE(S) case S: slot_update_w<S>(acc, w, b, -1, xa0, xa1, xb0, xb1, Lc, frag_off); break;
 #define PW_PICK(S) case S: p0 = acc[S][0]; p1 = acc[S][1]; break;
 #define PW_ALL(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
 
@@ -120,7 +107,6 @@ potf2_flow_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
     double *Lc = pw_dyn;                                 // every published 8x8 block of L11 (written once)
     double *W8c = pw_dyn + PW_LC_ELEMS;                  // the 16 diagonal 8x8 inverses
     __shared__ __align__(16) double sD[64];              // diagonal fragment on its way to the row-per-lane layout
-    __shared__ int f_lw, f_x[PW_NF];
     __shared__ int s_fail;
     const int item = blockIdx.x;
     if (A.count && item >= *A.count) return;
@@ -134,8 +120,7 @@ potf2_flow_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
     const int frag_off = fr * 8 + 2 * fk;
     const int rowA = w, rowB = PW_NF - 1 - w;
 
-    if (tid == 0) { s_fail = 0; f_lw = -1; }
-    if (tid < PW_NF) f_x[tid] = -1;
+    if (tid == 0) s_fail = 0;
     // ---- the block's lower fragments straight into registers (rows / columns beyond the matrix: identity)
     double acc[PW_SLOTS][2];
 #pragma unroll
@@ -202,21 +187,20 @@ potf2_flow_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
                 Wb[(size_t)(b * 8 + c) * NB + b * 8 + r8] = v[c];
             }
         }
-        __syncwarp();
-        if (lane == 0) flag_store(&f_lw, b);
     };
 
-    if (w == 0) factor_diag(0);
+    if (w == 0) { factor_diag(0); bar_arrive_n(1); }
 
 #pragma unroll 1
     for (int b = 0; b < PW_NF; ++b) {
+        const int par = b & 1;
+        const bool own = (b < PW_WARPS) ? (w == b) : (w == PW_NF - 1 - b);
+        if (!own) bar_sync_n(1 + par);                                              // P_b (its owner arrived when it published)
         // slot of (rowA, b): 2b while b < w;  slot of (rowB, b): 2b+1 while b <= w, then w+1+b while b < rowB
         const int slotA = (b < w) ? 2 * b : -1;
         const int slotB = (b <= w) ? 2 * b + 1 : ((b < rowB) ? w + 1 + b : -1);
-        if (slotB < 0) break;                                                       // both rows of this warp are finished
         // ------------------------------------------------------------------ B: my fragments of block column b
-        flag_wait_ge(&f_lw, b);
-        {
+        if (slotB >= 0) {
             const double2 wv = *reinterpret_cast<const double2 *>(&W8c[b * 64 + frag_off]);
             const double2 lv = *reinterpret_cast<const double2 *>(&Lc[(b * (b + 1) / 2 + b) * 64 + frag_off]);
             double a0, a1, b0, b1;
@@ -242,33 +226,42 @@ potf2_flow_kernel(BatchView A, int n, int j0, double *__restrict__ W, long long 
                 xa0 = x0; xa1 = x1;
                 *reinterpret_cast<double2 *>(&Lc[(rowA * (rowA + 1) / 2 + b) * 64 + frag_off]) = make_double2(x0, x1);
             }
-            __syncwarp();
-            if (lane == 0) { flag_store(&f_x[rowB], b); if (slotA >= 0) flag_store(&f_x[rowA], b); }
+        }
+        if (b + 1 == PW_NF) break;
+        // ------------------------------------------------------------------ the critical path: the owner of (b+1, b+1) updates
+        // that fragment (its own X on both sides) and factors it before anything else; everybody else goes on to phase C
+        int skip = -1;
+        const bool next_own = (b + 1 < PW_WARPS) ? (w == b + 1) : (w == PW_NF - 2 - b);
+        if (next_own) {
+            bar_arrive_n(3 + par);                                                  // X_b: my X(., b) are published
+            skip = (b + 1 < PW_WARPS) ? 2 * (b + 1) : PW_SLOTS - 1;
+            switch (skip) { PW_ALL(PW_ONE) default: break; }
+            factor_diag(b + 1);
+            bar_arrive_n(1 + (par ^ 1));                                            // P_{b+1}
+            bar_sync_n(5 + par);                                                    // Q_b: the others' X(., b) are visible to me
+        } else {
+            bar_sync_n(3 + par);                                                    // X_b
+            bar_arrive_n(5 + par);                                                  // Q_b
+        }
+        // the finished fragments of block column b leave for global memory off the critical path
+        if (slotB >= 0) {
             {
                 const int gr = rowB * 8 + fr, gc = b * 8 + 2 * fk;
                 if (gr < nv) {
-                    if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(y0, y1);
-                    else if (gc < nv) Ab[(size_t)gr * ld + gc] = y0;
+                    if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(xb0, xb1);
+                    else if (gc < nv) Ab[(size_t)gr * ld + gc] = xb0;
                 }
             }
             if (slotA >= 0) {
                 const int gr = rowA * 8 + fr, gc = b * 8 + 2 * fk;
                 if (gr < nv) {
-                    if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(x0, x1);
-                    else if (gc < nv) Ab[(size_t)gr * ld + gc] = x0;
+                    if (gc + 1 < nv) *reinterpret_cast<double2 *>(Ab + (size_t)gr * ld + gc) = make_double2(xa0, xa1);
+                    else if (gc < nv) Ab[(size_t)gr * ld + gc] = xa0;
                 }
             }
         }
-        // ------------------------------------------------------------------ the critical path: the owner of (b+1, b+1) updates
-        // that fragment (its own X on both sides) and factors it before anything else
-        int skip = -1;
-        if (b + 1 < PW_NF && ((b + 1 < PW_WARPS) ? (w == b + 1) : (w == PW_NF - 2 - b))) {
-            skip = (b + 1 < PW_WARPS) ? 2 * (b + 1) : PW_SLOTS - 1;
-            switch (skip) { PW_ALL(PW_ONE) default: break; }
-            factor_diag(b + 1);
-        }
         // ------------------------------------------------------------------ C: my other live fragments (c > b): a suffix of the slots
-        {
+        if (slotB >= 0) {
             const int start = (b + 1 <= w) ? 2 * (b + 1) : w + b + 2;
             switch (start) { PW_ALL(PW_CASE) default: break; }
         }

@@ -41,6 +41,20 @@ class OracleSweeper(object):
         return self.F.copy(), self.H.copy()
 
 
+class OracleRunSweeper(OracleSweeper):
+    """The same double with the `run` method of the device sweeper (many iterations per call, history as tensors), so
+    that ChainEnsemble.run takes its block path: one all-gather of [n_local, k, P + 2] per block of iterations."""
+
+    def run(self, it0, n_iters, thin_f=0, thin_phase=0):
+        hh = np.zeros((self.H.shape[0], n_iters, self.H.shape[1]))
+        ll = np.zeros((self.H.shape[0], n_iters))
+        nt = np.zeros((self.H.shape[0], n_iters), dtype=np.int64)
+        for k in range(n_iters):
+            H, l, t = self.sweep(it0 + k)
+            hh[:, k, :], ll[:, k], nt[:, k] = H, l, t
+        return torch.tensor(hh), torch.tensor(ll), torch.tensor(nt), None, 0
+
+
 def main():
     dist.init_process_group('gloo')
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -65,6 +79,10 @@ def main():
     assert ens2.n_chains == B and (ens2.lo, ens2.hi) == (lo, hi)
     h2, _, _ = ens2.sweep(0)
     assert np.array_equal(h2, hist[:, :, 0])
+    # block path of ChainEnsemble.run (what the device sweeper uses): history gathered per block of iterations
+    ens3 = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=7, sweeper=OracleRunSweeper(x, y, scale, 7, lo))
+    h3, l3, t3 = ens3.run(iters, gather_every=2)
+    assert np.array_equal(h3, hist) and np.array_equal(l3, ll) and np.array_equal(t3, trips)
     dist.barrier()
     if rank == 0:
         print('GLOO_OK shards=%s' % [gp.chains.shard_bounds(B, world, r) for r in range(world)])
