@@ -12,10 +12,16 @@
 //     Q_b  "... and visible to owner(b+1)"        the other warps: bar.arrive (right after X_b)   owner(b+1): bar.sync,
 //                                                  after it has factored -- by then the others are long past it
 // Every solved fragment X(r, c) and every L8 / W8 is written ONCE to its own place in shared memory (the lower 8x8 blocks
-// of L11, 76 KB -- the layout the fused panel solve needs anyway), so there are no write-after-read hazards.  A first
-// version synchronised with flags in shared memory (st.release / spinning ld.acquire): 38.6 us per block against the
-// 34.8 us of potf2_reg.cu -- the fences and the spinning warps cost more than the barriers they replaced.
+// of L11, 76 KB -- the layout the fused panel solve needs anyway), so there are no write-after-read hazards.
 // Results are bit-identical to potf2_reg.cu (same operations on the same operands, only their interleaving changes).
+//
+// MEASURED, and therefore NOT the default (gpmc_set_tuning(1, 3) selects it): 39.3 us per block / 579 us per 4096 blocks
+// against 35.1 / 512 for potf2_reg.cu; a first version synchronised with flags in shared memory (st.release, spinning
+// ld.acquire) gave 38.6 / 585.  Overlapping the single-warp factor step with the other warps' work does not pay here:
+// the stall samples of potf2_reg.cu are spread evenly over its ~550 straight-line instructions per factor step at ~3.7
+// cycles each, shortening the pivot chain changed nothing, and every variant that makes more warps execute different
+// code at the same time (this one, or walking the update suffix twice) got slower -- the signature of a kernel that is
+// bound by instruction issue / fetch of long unrolled code, not by the dependency chain the restructuring shortens.
 #include "common.cuh"
 #include "../../include/gpmc.h"
 
