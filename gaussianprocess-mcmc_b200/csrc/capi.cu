@@ -5,13 +5,17 @@
 
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 #include <algorithm>
 #include <vector>
 
 namespace gpmc {
 
 // ------------------------------------------------------------------------------------ error text
-static char g_err[1024] = "";
+static thread_local char g_err[1024] = "";          // the text belongs to the thread whose call failed
+static std::recursive_mutex g_api_mutex;
+ApiLock::ApiLock() { g_api_mutex.lock(); }
+ApiLock::~ApiLock() { g_api_mutex.unlock(); }
 void set_error(const char *fmt, ...)
 {
     va_list ap;
@@ -192,6 +196,7 @@ size_t gpmc_workspace_bytes(int op, int N, int D, int B)
 int gpmc_cov_assemble(const double *x_dev, int N, int D, const double *hyp_dev, int B, int P, int kind, int flags,
                       const double *jitter_dev, double *A_dev, int ld, void *stream)
 {
+    GPMC_API_LOCK();
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2) { set_error("cov_assemble: bad shape N=%d D=%d B=%d P=%d kind=%d", N, D, B, P, kind); return GPMC_EINVAL; }
     if (ld < N || (ld & 1)) { set_error("cov_assemble: ld=%d must be even and >= N=%d", ld, N); return GPMC_EALIGN; }
@@ -202,6 +207,7 @@ int gpmc_cov_assemble(const double *x_dev, int N, int D, const double *hyp_dev, 
 int gpmc_potrf_batched(double *A_dev, int N, int ld, int B, int *info_dev, int jitter_policy, int zero_upper,
                        void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     if (N <= 0 || B < 0) { set_error("potrf: bad shape N=%d B=%d", N, B); return GPMC_EINVAL; }
     if (B == 0) return 0;
@@ -276,6 +282,7 @@ int gpmc_loglik_batched(const double *x_dev, int N, int D, const double *g_dev, 
                         int kind, int jitter_policy, double *loglik_dev, int *info_dev, void *ws_dev, size_t ws_bytes,
                         void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2) { set_error("loglik: bad shape N=%d D=%d B=%d P=%d kind=%d", N, D, B, P, kind); return GPMC_EINVAL; }
@@ -340,6 +347,7 @@ static int ensure(void **p, size_t *have, size_t need, bool pinned)
 int gpmc_loglik_host(const double *x_host, int N, int D, const double *g_host, const double *hyp_host, int B, int P,
                      int kind, int jitter_policy, double *loglik_host, int *info_host)
 {
+    GPMC_API_LOCK();
     if (N <= 0 || D <= 0 || B <= 0) { set_error("loglik_host: bad shape"); return GPMC_EINVAL; }
     if (!g_hp.stream) GPMC_CUDA_CHECK(cudaStreamCreateWithFlags(&g_hp.stream, cudaStreamNonBlocking));
     cudaStream_t s = g_hp.stream;
@@ -381,6 +389,7 @@ int gpmc_loglik_host(const double *x_host, int N, int D, const double *g_host, c
 
 int gpmc_bench_fp64_peak(int which, int iters, double *tflops_out, double *ms_out)
 {
+    GPMC_API_LOCK();
     double tf = 0.0, ms = 0.0;
     const int rc = run_fp64_peak(which, iters, &tf, &ms);
     if (tflops_out) *tflops_out = tf;
@@ -390,6 +399,7 @@ int gpmc_bench_fp64_peak(int which, int iters, double *tflops_out, double *ms_ou
 
 int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_out)
 {
+    GPMC_API_LOCK();
     double tf = 0.0;
     const int rc = run_dmma_ilp(nacc, warps_per_sm, iters, &tf);
     if (tflops_out) *tflops_out = tf;
@@ -398,6 +408,7 @@ int gpmc_bench_dmma_ilp(int nacc, int warps_per_sm, int iters, double *tflops_ou
 
 int gpmc_set_tuning(int key, int value)
 {
+    GPMC_API_LOCK();
     if (key == 0) { set_gemm_config(value); return 0; }
     if (key == 1) { set_potf2_mode(value); return 0; }
     if (key == 2) { set_lookahead_mode(value); return 0; }
@@ -413,20 +424,23 @@ int gpmc_set_tuning(int key, int value)
 
 int gpmc_sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders)
 {
+    GPMC_API_LOCK();
     sds_loop_stats(rounds, idle_rounds, ladders);
     return 0;
 }
 
-int gpmc_profile_enable(int on) { g_prof_on = (on != 0); return 0; }
+int gpmc_profile_enable(int on) { GPMC_API_LOCK(); g_prof_on = (on != 0); return 0; }
 
 int gpmc_profile_reset(void)
 {
+    GPMC_API_LOCK();
     for (int k = 0; k < KC_COUNT; ++k) g_used[k] = 0;
     return 0;
 }
 
 int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches)
 {
+    GPMC_API_LOCK();
     if (kernel_class < 0 || kernel_class >= KC_COUNT) return GPMC_EINVAL;
     GPMC_CUDA_CHECK(cudaDeviceSynchronize());
     double tot = 0.0;

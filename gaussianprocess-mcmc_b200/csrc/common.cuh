@@ -19,6 +19,10 @@ constexpr int MAX_BATCH_ITEMS = 32768;   // batch items of one launch ride in gr
 enum KernelClass { KC_ASSEMBLE = 0, KC_GEMM = 1, KC_POTF2 = 2, KC_TRSM = 3, KC_SOLVE = 4, KC_INV = 5, KC_SYRK_R = 6, KC_VEC = 7, KC_COUNT = 8 };
 
 void set_error(const char *fmt, ...);
+// Every computing entry point of the C ABI takes this (recursive) lock: the library keeps per-process state (side streams,
+// staging buffers, tuning switches), so calls from several host threads are SERIALISED rather than racing.
+struct ApiLock { ApiLock(); ~ApiLock(); };
+#define GPMC_API_LOCK() gpmc::ApiLock _gpmc_api_lock
 void prof_begin(int kc, cudaStream_t s);
 void prof_end(int kc, cudaStream_t s);
 

@@ -49,6 +49,7 @@ extern "C" {
 int gpmc_cov_cross(const double *x_dev, int N, const double *z_dev, int M, int D, const double *hyp_dev, int P, int kind,
                    double *out_dev, int ld, void *stream)
 {
+    GPMC_API_LOCK();
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || M <= 0 || D <= 0 || D > MAX_ELL || P != n_ell + 2 || ld < M) {
         set_error("cov_cross: bad shape N=%d M=%d D=%d P=%d kind=%d ld=%d", N, M, D, P, kind, ld);
@@ -63,6 +64,7 @@ int gpmc_cov_cross(const double *x_dev, int N, const double *z_dev, int M, int D
 int gpmc_tg2_loglik(const double *y_dev, double my, const double *mu_dev, int ldmu, int N, int B, const double *sn_dev,
                     double lower, double upper, double *out_dev, void *stream)
 {
+    GPMC_API_LOCK();
     if (N <= 0 || B < 0 || ldmu < N) { set_error("tg2_loglik: bad shape N=%d B=%d ldmu=%d", N, B, ldmu); return GPMC_EINVAL; }
     if (B == 0) return 0;
     tg2_loglik_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(y_dev, my, mu_dev, ldmu, N, sn_dev, lower, upper, out_dev);

@@ -205,6 +205,7 @@ int gpmc_predict_batched(const double *x_dev, int N, int D, const double *xs_dev
                          int S, int P, int kind, int jitter_policy, double *fmu_dev, double *fs2_dev, int *info_dev,
                          void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || D > MAX_ELL || M <= 0 || S < 0 || P != n_ell + 2) {
@@ -269,6 +270,7 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
                    int max_trips, int jitter_policy, int *ntrips_dev, int *status_dev, int *info_dev,
                    void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || D > MAX_ELL || B < 0 || P != n_ell + 2 || max_trips <= 0 || (tape_theta && tape_trips < 1)) {

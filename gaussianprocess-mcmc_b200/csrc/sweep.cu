@@ -625,6 +625,7 @@ size_t gpmc_aux_workspace_bytes(int N)
 int gpmc_aux_var_model(const double *K_dev, int N, int ld, const double *S_dev, const double *g_dev, double *L_dev,
                        double *m_dev, double *C_dev, int *info_dev /*[2]*/, void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     if (N <= 0 || ld < N || (ld & 15)) { set_error("aux_var_model: need ld %% 16 == 0 and ld >= N (N=%d ld=%d)", N, ld); return GPMC_EALIGN; }
     if (!ws_dev || ws_bytes < gpmc_aux_workspace_bytes(N)) { set_error("aux_var_model: workspace too small"); return GPMC_ENOMEM; }
@@ -661,6 +662,7 @@ int gpmc_aux_var_model(const double *K_dev, int N, int ld, const double *S_dev, 
 int gpmc_trsv_lower_batched(const double *L_dev, int N, int ld, long long strideL, const double *rhs_dev, int ldv, int B,
                             double *out_dev, double *quad_dev, void *stream)
 {
+    GPMC_API_LOCK();
     if (N <= 0 || B < 0 || ld < N || (ld & 1) || (ldv & 1) || ldv < N) { set_error("trsv: bad shape N=%d ld=%d ldv=%d B=%d", N, ld, ldv, B); return GPMC_EINVAL; }
     BatchView Lv{const_cast<double *>(L_dev), strideL, ld, nullptr, nullptr};
     // quad_dev (optional) receives -(0.5 x.x + sum log L_ii + 0.5 N log 2pi), i.e. log N(b; 0, L L^T)
@@ -673,6 +675,7 @@ int gpmc_sds_run(const double *x_dev, const double *y_dev, int N, int D, double 
                  double *hist_hyp_dev, double *hist_loglik_dev, int *hist_trips_dev, double *hist_f_dev, int thin, int n_keep,
                  int *n_exhausted_dev, void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2 || max_trips <= 0 || n_iters < 0 || (hist_f_dev && (thin <= 0 || n_keep <= 0))) {
@@ -703,6 +706,7 @@ int gpmc_sds_run(const double *x_dev, const double *y_dev, int N, int D, double 
 
 size_t gpmc_sds_workspace_bytes(int N, int P, int chains_per_wave)
 {
+    GPMC_API_LOCK();
     if (N <= 0 || P < 3 || chains_per_wave <= 0) return 0;
     return sweep_bytes(N, P, chains_per_wave);
 }
@@ -714,6 +718,7 @@ int gpmc_sds_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
                    int max_trips, int jitter_policy, int *ntrips_dev, double *loglik_dev, int *status_dev,
                    void *ws_dev, size_t ws_bytes, void *stream)
 {
+    GPMC_API_LOCK();
     cudaStream_t s = (cudaStream_t)stream;
     const int n_ell = (kind == GPMC_KIND_SE_ARD) ? D : 1;
     if (N <= 0 || D <= 0 || B < 0 || P != n_ell + 2 || max_trips <= 0) {

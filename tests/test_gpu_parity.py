@@ -519,3 +519,27 @@ def test_fused_panel_launches_in_the_sds_sweep(gp):
         np.testing.assert_allclose(b[1], a[1], rtol=1e-12)
         np.testing.assert_allclose(b[3], a[3], rtol=1e-10)
         assert np.abs(a[0] - b[0]).max() < 5e-2
+
+
+def test_two_host_threads_are_serialised_not_racing(gp, so):
+    """The library keeps per-process state (side streams, staging buffers): every computing entry point of the C ABI takes a
+    recursive lock, so two host threads (ctypes drops the GIL during the calls) get correct, identical results."""
+    import threading
+    n = 300
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(24, n)
+    want, _ = gp.ops.loglik_host(x, G, H)
+    out = {}
+
+    def work(k):
+        res = []
+        for _ in range(6):
+            ll, info = gp.ops.loglik_host(x, G[k::2], H[k::2])
+            res.append(ll)
+        out[k] = res
+    ts = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in (0, 1):
+        for ll in out[k]:
+            assert np.array_equal(ll, want[k::2])
