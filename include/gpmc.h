@@ -26,15 +26,17 @@
  *    with E = 1 (GPMC_KIND_SE_ISO, the reference's covK.RBF) or E = D
  *    (GPMC_KIND_SE_ARD); P = E + 2.
  *  - threading: like the reference (one Python thread, sliceSample.py uses the
- *    global numpy RNG) the library is meant for ONE host thread per process and
+ *    global numpy RNG) the library is meant for one host thread per process and
  *    one process per GPU; it keeps per-process state (side streams and events of
  *    the look-ahead schedule, the host-path staging buffers, the pinned status
- *    ring of the resident sampler loop -- one per device --, the last-error text)
- *    and is not re-entrant.  Kernel attributes are set per device, so one thread
- *    may drive several devices in turn.  Calls are asynchronous on `stream`
- *    except where a jitter policy needs info[] on the host (one synchronisation
- *    per wave) and inside gpmc_sds_sweep / gpmc_sds_run, which return when the
- *    last chain has finished (the host polls a status word meanwhile).
+ *    ring of the resident sampler loop -- one per device --, tuning switches).
+ *    Every computing entry point takes a process-wide recursive lock, so calls
+ *    from several host threads are SERIALISED, not racing; gpmc_last_error() is
+ *    per thread; kernel attributes are set per device, so a thread may drive
+ *    several devices in turn.  Calls are asynchronous on `stream` except where a
+ *    jitter policy needs info[] on the host (one synchronisation per wave) and
+ *    inside gpmc_sds_sweep / gpmc_sds_run, which return when the last chain has
+ *    finished (the host polls a status word meanwhile).
  */
 #ifndef GPMC_H
 #define GPMC_H
