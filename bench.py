@@ -389,7 +389,7 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     return rec
 
 
-def sub_c1(gp, np, iters=30, cpu_iters=6, literal=False):
+def sub_c1(gp, np, iters=30, cpu_iters=20, literal=False):
     """BASELINE config 1 (demoRegression.py: N=200, one chain): the reference's caller loop (demoRegression.py:23-30) on
     the drop-in `kcMCMC.sliceSample.surrogate_slice_sampling`, host arrays in / out, global numpy stream seeded like the
     reference (seed 124, hyp0 = [0.35, 2.0, 0.2]); the CPU oracle consumes the same stream beside it."""
@@ -548,6 +548,8 @@ def run_b200(args):
             if world == 1:
                 if on('C1_chain'):
                     configs.append(sub_c1(gp, np))
+                if on('C1_chain_literalR'):
+                    configs.append(sub_c1(gp, np, literal=True))
                 if on('C2_loglik'):
                     configs.append(sub_loglik(gp, torch, np, 'C2_loglik', 2048, 64, 0, 10, peak_tf, 8,
                                               'BASELINE config 2: IH45-shaped series, N=2048, SE+noise, 64 chains, 1 B200'))

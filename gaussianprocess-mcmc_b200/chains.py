@@ -106,6 +106,32 @@ class ChainEnsemble(object):
     def local_state(self):
         return self._sweeper.state()
 
+    # ---- checkpoint / resume (the reference only writes CSV files at the very end, framework.py:79-122: a crash loses the
+    # chain).  Randomness is keyed by (seed, global chain id, iteration), so the state of a run is just (f, theta) of every
+    # chain plus the next iteration: a resumed run continues bit for bit.
+    def save(self, path, next_iter):
+        """Write this rank's shard (``<path>.rank<r>.npz``): chain states, shard bounds, seed, next iteration."""
+        F, H = self.local_state()
+        np.savez(('%s.rank%d.npz' % (path, self.rank)), F=F, H=H, lo=self.lo, hi=self.hi, n_chains=self.n_chains,
+                 seed=self.seed, next_iter=int(next_iter), scale=self.scale, max_trips=self.max_trips)
+
+    @classmethod
+    def resume(cls, path, x, y, **kw):
+        """Rebuild the ensemble from files written by :meth:`save` (same number of ranks).  Returns ``(ensemble, next_iter)``."""
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except ImportError:
+            pass
+        z = np.load('%s.rank%d.npz' % (path, rank))
+        ens = cls(x, y, z['F'], z['H'], z['scale'], seed=int(z['seed']), max_trips=int(z['max_trips']), sharded_input=True, **kw)
+        if (ens.lo, ens.hi, ens.n_chains) != (int(z['lo']), int(z['hi']), int(z['n_chains'])):
+            raise ValueError('checkpoint was written with a different sharding: [%d, %d) of %d, now [%d, %d) of %d' % (
+                int(z['lo']), int(z['hi']), int(z['n_chains']), ens.lo, ens.hi, ens.n_chains))
+        return ens, int(z['next_iter'])
+
     def _gather(self, hyp, ll, nt, status=None):
         import torch
         P = self.P

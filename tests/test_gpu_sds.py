@@ -514,3 +514,23 @@ def test_literal_R_mode_matches_reference(gp, path):
     print('%s: literal-R device |f - f_ref| %.2e; reference resolution (BLAS order / 1-ulp K) %.2e; |f| ~ %.2f' % (
         os.path.basename(path), err, spread, np.abs(z['ref_prop_f']).max()))
     assert err <= max(1e-6, 20.0 * spread), (err, spread)
+
+
+def test_checkpoint_resume_continues_bit_for_bit(gp, tmp_path):
+    """ChainEnsemble.save / resume: randomness is keyed by (seed, chain, iteration), so an interrupted run continued from
+    its checkpoint equals the uninterrupted run bit for bit (the reference has no checkpoint: a crash loses the chain)."""
+    n, B = 96, 9
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array(gp.synthetic.SCALE)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    full = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=21, max_trips=48)
+    hist, ll, trips = full.run(6, start_iter=497)
+    part = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=21, max_trips=48)
+    h1, l1, t1 = part.run(2, start_iter=497)
+    part.save(str(tmp_path / 'ck'), next_iter=499)
+    res, it = gp.chains.ChainEnsemble.resume(str(tmp_path / 'ck'), x, y)
+    assert it == 499
+    h2, l2, t2 = res.run(4, start_iter=it)
+    assert np.array_equal(np.concatenate([h1, h2], axis=2), hist)
+    assert np.array_equal(np.concatenate([l1, l2], axis=1), ll) and np.array_equal(np.concatenate([t1, t2], axis=1), trips)
+    assert np.array_equal(res.local_state()[0], full.local_state()[0])
