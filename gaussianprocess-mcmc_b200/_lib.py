@@ -57,6 +57,7 @@ SIGNATURES = {
     'gpmc_profile_enable': (_i, [_i]),
     'gpmc_profile_read': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     'gpmc_profile_reset': (_i, []),
+    'gpmc_profile_timeline': (_i, [_i, _i, ctypes.POINTER(ctypes.c_double), ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong)]),
 }
 
 _lib = None

@@ -454,4 +454,26 @@ int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches)
     return 0;
 }
 
+// every recorded launch of one class as (start, end) in ms after `origin_class`'s first launch began (its order in the
+// returned list is the order of the launches); returns the number of intervals written
+int gpmc_profile_timeline(int kernel_class, int origin_class, double *start_end_ms, long long capacity, long long *written)
+{
+    GPMC_API_LOCK();
+    if (kernel_class < 0 || kernel_class >= KC_COUNT || origin_class < 0 || origin_class >= KC_COUNT || !start_end_ms || !written)
+        return GPMC_EINVAL;
+    if (g_used[origin_class] == 0) { set_error("gpmc_profile_timeline: no launch of the origin class recorded"); return GPMC_EINVAL; }
+    GPMC_CUDA_CHECK(cudaDeviceSynchronize());
+    const cudaEvent_t t0 = g_pool[origin_class][0].a;
+    long long w = 0;
+    for (size_t i = 0; i < g_used[kernel_class] && w < capacity; ++i, ++w) {
+        float a = 0.f, b = 0.f;
+        GPMC_CUDA_CHECK(cudaEventElapsedTime(&a, t0, g_pool[kernel_class][i].a));
+        GPMC_CUDA_CHECK(cudaEventElapsedTime(&b, t0, g_pool[kernel_class][i].b));
+        start_end_ms[2 * w] = a;
+        start_end_ms[2 * w + 1] = b;
+    }
+    *written = w;
+    return 0;
+}
+
 }  // extern "C"

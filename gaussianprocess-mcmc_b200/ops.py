@@ -513,6 +513,21 @@ def profile(on):
     lib.gpmc_profile_enable(1 if on else 0)
 
 
+def profile_timeline(origin='assemble', capacity=65536):
+    """{class name: float64[launches, 2]} -- (start, end) of every recorded launch in ms after the first launch of
+    class ``origin`` began.  Streams of the look-ahead schedule overlap in time."""
+    lib = _lib.load()
+    o = _lib.KC_NAMES.index(origin)
+    out = {}
+    for k, name in enumerate(_lib.KC_NAMES):
+        buf = np.zeros((capacity, 2))
+        n = ctypes.c_longlong()
+        _lib.check(lib.gpmc_profile_timeline(k, o, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), capacity, ctypes.byref(n)),
+                   'gpmc_profile_timeline')
+        out[name] = buf[:n.value].copy()
+    return out
+
+
 def profile_read():
     """{class name: (total_ms, launches)} of the library's own kernels since the last reset."""
     lib = _lib.load()

@@ -270,6 +270,9 @@ int gpmc_sds_loop_stats(long long *rounds, long long *idle_rounds, long long *la
 int gpmc_profile_enable(int on);
 int gpmc_profile_read(int kernel_class, double *total_ms, long long *launches);
 int gpmc_profile_reset(void);
+/* Debug: every recorded launch of `kernel_class` as (start, end) pairs in ms, measured from the start of the first
+ * recorded launch of `origin_class` (launch order; look-ahead streams overlap in time). */
+int gpmc_profile_timeline(int kernel_class, int origin_class, double *start_end_ms, long long capacity, long long *written);
 
 #ifdef __cplusplus
 }
