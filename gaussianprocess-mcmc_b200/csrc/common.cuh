@@ -172,7 +172,8 @@ int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const 
 
 // sweep.cu
 void set_sds_mode(int mode);       // 0: resident loop (default), 1: wave loop
-void set_panel_fuse(int mode);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
+void set_panel_fuse(int mode);
+void set_lookahead_split(int mode);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
 void set_sds_literal(int v);       // 1: R = K - V^T V as the reference writes it (parity), 0: reduced form (default)
 void set_sds_runahead(int r);      // rounds queued ahead of the last status word seen (0: auto)
 void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);

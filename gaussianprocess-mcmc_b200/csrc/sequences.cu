@@ -227,6 +227,12 @@ static LookAhead *lookahead_ctx()
 static int g_lookahead_mode = 0;       // 0 auto (B <= #SMs / 2), 1 off, 2 on
 void set_lookahead_mode(int mode) { g_lookahead_mode = mode; }
 
+// In-window update of a look-ahead column: split in a long part (runs beside the previous column's panel kernels) and a
+// K = 128 short part, or one launch after the previous column's panel solve.  0 auto, 1 always split, 2 never split a
+// window that has no trailing update running beside it.
+static int g_split_mode = 0;
+void set_lookahead_split(int mode) { g_split_mode = mode; }
+
 static int g_panel_fuse = 0;           // 0 auto, 1 never, 2 whenever the default panel kernels are selected
 void set_panel_fuse(int mode) { g_panel_fuse = mode; }
 
@@ -310,12 +316,26 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
                 if ((rc = extra_rows_update(w1, n - w1, w0 - wlen, wlen, sG))) return rc;
             }
         }
+        // A window with a trailing update running beside it keeps the split (the panel factor kernel is slowed several
+        // times by co-resident update CTAs and hides behind the long part).  The first and the last window run alone:
+        // when their launches fill the chip several times over anyway, the two K-short launches (23 TFLOP/s at K = 128)
+        // cost more than the 35 us of an exposed panel factor kernel (tools/timeline.py).
+        const bool paired = w0 > 0 && w1 < n;
+        const bool many_ctas = (long long)B * ((n - w0 + 127) / 128) * 2 >= 8LL * sm_count();
+        const bool split_cols = la && (g_split_mode == 1 || paired || (g_split_mode == 0 && !many_ctas));
         for (int j0 = w0; j0 < w1; j0 += NB) {
             const int width = std::min(NB, n - j0);
             double *Wj = W + (size_t)(j0 / NB) * w_step;
             int rc;
             if (!la) {
                 if (j0 > w0 && (rc = update(j0, width, w0, j0, s))) return rc;
+            } else if (!split_cols) {
+                if (j0 > w0) {
+                    GPMC_CUDA_CHECK(cudaStreamWaitEvent(sQ, la->ev_p, 0));                        // column j-1 solved
+                    if ((rc = update(j0, width, w0, j0, sQ))) return rc;
+                }
+                GPMC_CUDA_CHECK(cudaEventRecord(la->ev_q, sQ));
+                GPMC_CUDA_CHECK(cudaStreamWaitEvent(sP, la->ev_q, 0));
             } else {
                 if (j0 - NB > w0 && (rc = update(j0, width, w0, j0 - NB, sQ))) return rc;         // long part
                 if (j0 > w0) {

@@ -250,7 +250,10 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  *        sliceSample.py:197-198,204 write it (8/3 N^3; twice the workspace per chain -- query gpmc_sds_workspace_bytes
  *        after setting it).  Used for parity with the reference, not for speed.
  * key 9: panel factor + panel solve of a block column in ONE launch (one CTA per matrix): 0 = auto (many small matrices in
- *        flight), 1 = never, 2 = whenever the default panel kernels are selected. */
+ *        flight), 1 = never, 2 = whenever the default panel kernels are selected.
+ * key 10: in-window update of a look-ahead column: 0 = auto (split in a long and a K = 128 short part when a trailing update
+ *        runs beside the window or the launches are small; one launch otherwise), 1 = always split, 2 = one launch in every
+ *        window that runs alone. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
