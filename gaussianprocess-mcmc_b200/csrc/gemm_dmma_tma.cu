@@ -109,6 +109,18 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     if (tid == 0)      // lock step: one stage stays free for the refill; free running: all stages start full
         for (int s = 0; s < (FREE_RUNNING ? TSTAGES : TSTAGES - 1) && s < nk; ++s) issue(s);
 
+    // the epilogue subtracts from the C tile: ask L2 for its 512 lines now (two per thread), so that the loads at the
+    // end of the K loop do not wait for HBM -- matters for the short contractions only (K = 128 parts of the look-ahead,
+    // N = 512 matrices: +1 ... 1.5 %; long contractions hide the epilogue behind the co-resident CTA anyway)
+    if (p.epi == EPI_SUB && klen <= 512) {
+        const double *Cb = p.C.base + (size_t)m * p.C.stride + (size_t)(p.cr0 + tm * TBM) * p.C.ld + p.cc0 + tn * TBN;
+#pragma unroll
+        for (int e = tid; e < TBM * (TBN / 16); e += TTHREADS) {
+            const int r = e / (TBN / 16), c = (e % (TBN / 16)) * 16;
+            if (r < rows_valid && c < cols_valid) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Cb + (size_t)r * p.C.ld + c));
+        }
+    }
+
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int frow = lane >> 2, fk = lane & 3;
