@@ -263,3 +263,92 @@ def test_cross_validation_driver(gp, tmp_path):
     assert list(res) == [1] and len(res[1]) == 5 and np.all(np.isfinite(res[1]))
     assert os.path.isfile(os.path.join(str(tmp_path), 'hypGap1.csv')) and os.path.isfile(os.path.join(str(tmp_path), 'llkGap1.csv'))
     assert cv.x.shape[0] == n                                           # data restored
+
+
+def test_every_kernel_family_small_pass(gp):
+    """tools/sanitize_smoke.py: ragged single block, fused and separate panel kernels, look-ahead streams, every panel
+    kernel variant, ARD, resident / wave / run-mode / literal-R SDS, predictive path, elliptical slice, single-matrix
+    auxiliary model -- asserts finiteness and the cross-variant agreements the script states."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'sanitize_smoke.py')
+    spec = importlib.util.spec_from_file_location('sanitize_smoke', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main([])
+
+
+class _GuardedWorkspace(object):
+    """Workspace handed to the library as EXACTLY the bytes it asked for, with 1 MiB of sentinel bytes on both sides
+    (compute-sanitizer is not available on the GPU pool: this is the out-of-bounds check for the workspace carving)."""
+    GUARD = 1 << 20
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.raw = None
+        self.buf = None
+        self.nbytes = 0
+
+    def get(self, torch, nbytes):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        if self.raw is None or self.nbytes != nbytes:
+            self.check()
+            self.raw = torch.full((nbytes + 2 * self.GUARD,), 0xA5, dtype=torch.uint8, device='cuda')
+            self.nbytes = nbytes
+            self.buf = self.raw[self.GUARD:self.GUARD + nbytes]
+        return self.buf
+
+    def check(self):
+        if self.raw is None:
+            return
+        self.torch.cuda.synchronize()
+        lo, hi = self.raw[:self.GUARD], self.raw[self.GUARD + self.nbytes:]
+        assert bool((lo == 0xA5).all().item()), 'bytes BEFORE the workspace were written'
+        assert bool((hi == 0xA5).all().item()), 'bytes AFTER the workspace were written'
+
+
+@pytest.mark.parametrize('n,B', [(37, 3), (129, 2), (300, 7), (640, 3), (700, 2), (1000, 3), (257, 200)])
+def test_workspace_bounds_loglik_and_potrf(gp, n, B):
+    import torch
+    ws = _GuardedWorkspace(torch)
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(B, n)
+    ll, info = gp.ops.loglik_batched(torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(H).cuda(), workspace=ws)
+    ws.check()
+    ref, _ = gp.ops.loglik_host(x, G, H)
+    assert np.array_equal(ll.cpu().numpy(), ref)
+    # a smaller wave than the batch: the carving of a partial workspace
+    if B > 2:
+        ll2, _ = gp.ops.loglik_batched(torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(H).cuda(), workspace=ws, max_wave=2)
+        ws.check()
+        assert np.array_equal(ll2.cpu().numpy(), ref)
+    A = gp.ops.cov_assemble(x, H, add_S=True)
+    gp.ops.potrf_batched(A, n=n, jitter_policy=gp.JITTER_PYGPS, workspace=ws)
+    ws.check()
+
+
+@pytest.mark.parametrize('n,B,literal', [(48, 5, 0), (130, 9, 0), (96, 4, 1)])
+def test_workspace_bounds_sds_predict_ess(gp, n, B, literal):
+    import torch
+    ws = _GuardedWorkspace(torch)
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array([10., 10., 5.])
+    try:
+        gp.ops.set_tuning(8, literal)
+        F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+        gp.ops.sds_sweep(x, y, F, H, scale, 2, seed=3, workspace=ws)
+        ws.check()
+        gp.ops.sds_sweep(x, y, F, H, scale, 3, seed=3, workspace=ws, chains_per_wave=2)
+        ws.check()
+        gp.ops.sds_run(x, y, F, H, scale, 4, 2, seed=3, workspace=ws, keep_f_every=1)
+        ws.check()
+    finally:
+        gp.ops.set_tuning(8, 0)
+    xs = np.linspace(0.5, n + 3.5, 13).reshape(-1, 1)
+    fm = torch.tensor(F0 - F0.mean(axis=1, keepdims=True)).cuda()
+    gp.ops.predict_batched(np.asarray(x).reshape(-1, 1), xs, fm, torch.tensor(H0).cuda(), workspace=ws)
+    ws.check()
+    F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+    gp.ops.ess_sweep(x, y, F, H, it=1, seed=9, workspace=ws)
+    ws.check()
