@@ -31,6 +31,43 @@ def union(iv):
     return sum(b - a for a, b in out), out
 
 
+def sds_timeline(a):
+    import time
+    n, B = a.n, a.batch
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array([10., 10., 5.])
+    F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+    for it in range(3):
+        gp.ops.sds_sweep(x, y, F, H, scale, it, seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    trips = 0
+    for it in range(a.sds):
+        trips += int(gp.ops.sds_sweep(x, y, F, H, scale, 3 + it, seed=1)[0].sum().item())
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / a.sds
+    gp.ops.profile(True)
+    tr = int(gp.ops.sds_sweep(x, y, F, H, scale, 3 + a.sds, seed=1)[0].sum().item())
+    torch.cuda.synchronize()
+    tl = gp.ops.profile_timeline('vector_control')
+    gp.ops.profile(False)
+    iv = np.concatenate([v for v in tl.values() if len(v)])
+    end = iv[:, 1].max()
+    u, _ = union(iv)
+    print('N=%d x %d chains: %.3f ms per transition (wall, %.1f proposals per transition)' % (n, B, 1e3 * wall, trips / a.sds / B))
+    print('profiled transition: %d proposals, %d launches, first launch -> last end %.3f ms, kernels running %.3f ms (%.0f %%), median kernel %.1f us'
+          % (tr, len(iv), end, u, 100 * u / end, 1e3 * np.median(iv[:, 1] - iv[:, 0])))
+    for k, v in tl.items():
+        if len(v):
+            d = v[:, 1] - v[:, 0]
+            print('  %-16s launches %4d  sum %8.3f ms  median %6.1f us' % (k, len(v), d.sum(), 1e3 * np.median(d)))
+    if a.dump:
+        rows = sorted((v0, v1, k) for k, v in tl.items() for v0, v1 in v)
+        for v0, v1, k in rows:
+            print('%9.1f %9.1f  %7.1f us  %s' % (1e3 * v0, 1e3 * v1, 1e3 * (v1 - v0), k))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', type=int, default=16384)
@@ -38,11 +75,14 @@ def main():
     ap.add_argument('--tune', action='append', default=[], help='key=value for gpmc_set_tuning')
     ap.add_argument('--json', default=None)
     ap.add_argument('--dump', action='store_true', help='every launch, sorted by start')
+    ap.add_argument('--sds', type=int, default=0, help='time this many SDS transitions of --batch chains instead of a log-lik pass')
     a = ap.parse_args()
     for kv in a.tune:
         k, v = kv.split('=')
         gp.ops.set_tuning(int(k), int(v))
     n, B = a.n, a.batch
+    if a.sds:
+        return sds_timeline(a)
     x = np.arange(n, dtype=np.float64).reshape(n, 1)
     G, H = gp.synthetic.loglik_batch(B, n, n_ell=1)
     xd, Gd, Hd = torch.tensor(x).cuda(), torch.tensor(G).cuda(), torch.tensor(H).cuda()
