@@ -134,10 +134,11 @@ gemm_dmma_kernel(GemmArgs p)
 }
 
 bool gemm_tma_supported(const GemmArgs &a);
-int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cudaStream_t s);
+int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cudaStream_t s, bool persistent = false);
 
 // 0: 8 warps 128x128; 1: 16 warps 128x128; 2: 8 warps 128x64, two CTAs per SM (cp.async); 3: as 2, TMA-staged;
-// 4: TMA-staged with full/empty mbarrier pairs (no block barrier in the main loop)
+// 4: TMA-staged with full/empty mbarrier pairs (no block barrier in the main loop); 5: as 4, persistent CTAs that fetch
+// the next tile's first chunks during the current tile's tail (used for short contractions when 4 is selected: see below)
 static int g_gemm_cfg = 4;
 void set_gemm_config(int cfg) { g_gemm_cfg = cfg; }
 
@@ -168,10 +169,14 @@ int launch_gemm(const GemmArgs &a, int B, int kclass, cudaStream_t s)
     static bool env_read = false;
     if (!env_read) {            // GPMC_GEMM_CFG=0..3 selects the tile-kernel variant (experiments / A-B tests)
         const char *e = getenv("GPMC_GEMM_CFG");
-        if (e && e[0] >= '0' && e[0] <= '4') g_gemm_cfg = e[0] - '0';
+        if (e && e[0] >= '0' && e[0] <= '5') g_gemm_cfg = e[0] - '0';
         env_read = true;
     }
     const bool border_fusable = a.border_row == 0 || (a.skip_upper && a.epi == EPI_SUB && a.cr0 == a.cc0 && a.A.base == a.C.base);
+    // persistent form: every tile needs at least one chunk, and the tile count must fit the scheduler's 32-bit words
+    const bool persist_ok = !a.k_follow_row && a.klen >= 1 &&
+                            (long long)((a.rows + 127) / 128 + 1) * ((a.cols + 63) / 64 + 1) * B < 0x70000000LL;
+    if (g_gemm_cfg == 5 && persist_ok && gemm_tma_supported(a) && border_fusable) return launch_gemm_tma(a, B, kclass, true, s, true);
     if (g_gemm_cfg == 4 && gemm_tma_supported(a) && border_fusable) return launch_gemm_tma(a, B, kclass, true, s);   // border row fused in-kernel
     if (a.border_row > 0) {
         // the other variants have no border duty: take the row along as one more output row (it follows the matrix)

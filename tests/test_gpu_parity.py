@@ -405,10 +405,11 @@ def test_loglik_random_shapes_against_oracle(gp, so):
     print('random shapes: worst error / tolerance', worst)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
 def test_every_tile_kernel_variant_factors_correctly(gp, so, cfg):
-    """The DMMA tile kernel exists in four variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
-    per SM, TMA-staged 128x64); all must give the same factor."""
+    """The DMMA tile kernel exists in several variants (cp.async 128x128 with 8 or 16 warps, cp.async 128x64 with two CTAs
+    per SM, TMA-staged 128x64 in lock step / free running / persistent with in-order tile hand-out); all must give the
+    same factor."""
     import scipy.linalg
     n = 700
     x = np.arange(n, dtype=np.float64).reshape(n, 1)
@@ -543,3 +544,23 @@ def test_two_host_threads_are_serialised_not_racing(gp, so):
     for k in (0, 1):
         for ll in out[k]:
             assert np.array_equal(ll, want[k::2])
+
+
+@pytest.mark.parametrize('n,B', [(300, 9), (512, 700), (1000, 3), (2500, 1), (129, 40)])
+def test_persistent_tile_kernel_is_bit_identical(gp, n, B):
+    """gemm_dmma_tma_persistent_kernel (tuning key 0 = 5: persistent CTAs, tiles drawn in order from a global counter,
+    next tile's first chunks fetched during the current tile's tail) computes every tile exactly as the default kernel
+    does, whatever order the tiles are handed out in -- including under the look-ahead streams (few matrices) and with
+    far more tiles than CTAs (many matrices); repeated launches reuse the scheduler ring."""
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(B, n)
+    ref, info = gp.ops.loglik_host(x, G, H)
+    assert np.all(info == 0)
+    try:
+        gp.ops.set_tuning(0, 5)
+        for _ in range(3):
+            ll, info = gp.ops.loglik_host(x, G, H)
+            assert np.all(info == 0)
+            assert np.array_equal(ll, ref)
+    finally:
+        gp.ops.set_tuning(0, 4)
