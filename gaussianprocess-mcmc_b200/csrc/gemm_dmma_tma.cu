@@ -17,7 +17,6 @@
 
 #include <cuda.h>
 #include <algorithm>
-#include <cstdlib>
 #include <type_traits>
 #include <cudaTypedefs.h>
 
@@ -569,7 +568,6 @@ int launch_gemm_tma(const GemmArgs &a, int B, int kclass, bool free_running, cud
             int dev = 0, sms = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
             slots = 2 * sms;
-            if (const char *e = getenv("GPMC_GEMM_SLOTS")) { const long long v = atoll(e); if (v > 0) slots = (int)std::min<long long>(v, 0x7fffffff); }   // experiments
         }
         const long long total = (long long)tiles * B;
         // scheduler words: a ring of (next tile, finished CTAs) pairs per device, every launch takes the next pair; the

@@ -233,6 +233,8 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
                    void *ws_dev, size_t ws_bytes, void *stream);
 
 /* Kernel tuning knobs for experiments.
+ * (Environment, read once: GPMC_GEMM_CFG=<key 0 value> preselects the tile kernel variant; GPMC_DEBUG=1 makes the SDS loops
+ *  print their round counters to stderr.)
  * key 0: DMMA tile kernel variant (0/1/2 cp.async staged, 3 TMA lock-step, 4 TMA free-running = default, 5 = 4 with
  *        persistent CTAs drawing tiles in order from a global counter: measured slower, kept for A/B).
  * key 1: panel factor kernel (0 = the register-resident kernel potf2_reg.cu (default), 3 = the same fragments as a dataflow
