@@ -209,8 +209,13 @@ struct LookAhead {
 };
 static LookAhead *lookahead_ctx()
 {
-    static LookAhead la;
-    static bool tried = false;
+    // streams and events belong to a device: one set per device ordinal
+    static LookAhead las[64];
+    static bool tried_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    LookAhead &la = las[dev];
+    bool &tried = tried_dev[dev];
     if (!tried) {
         tried = true;
         int lo = 0, hi = 0;
