@@ -420,6 +420,7 @@ int gpmc_set_tuning(int key, int value)
     if (key == 8) { set_sds_literal(value); return 0; }
     if (key == 9) { set_panel_fuse(value); return 0; }
     if (key == 10) { set_lookahead_split(value); return 0; }
+    if (key == 11) { set_inverse_window(value); return 0; }
     return GPMC_EINVAL;
 }
 

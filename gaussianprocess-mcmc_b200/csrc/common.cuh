@@ -92,7 +92,8 @@ enum Epilogue {
     EPI_SUB = 0,           // C = C - acc            (Cholesky update)
     EPI_SET = 1,           // C = acc                (panel TRSM via inverse; Y = U L^T)
     EPI_NEGSET = 2,        // C = -acc               (block column of U = L^-T)
-    EPI_R = 3              // C = S - S acc S (+1e-11 on the diagonal), S = diag(svec)   (posterior covariance R)
+    EPI_R = 3,             // C = S - S acc S (+1e-11 on the diagonal), S = diag(svec)   (posterior covariance R)
+    EPI_ADD = 4            // C = C + acc            (windowed triangular inverse: Y accumulated window by window)
 };
 struct GemmArgs {
     BatchView C;           // output matrices; its map/count select the batch items of the launch
@@ -173,7 +174,8 @@ int launch_trmv(BatchView T, int n, int upper, int mode, const double *x, const 
 // sweep.cu
 void set_sds_mode(int mode);       // 0: resident loop (default), 1: wave loop
 void set_panel_fuse(int mode);
-void set_lookahead_split(int mode);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
+void set_lookahead_split(int mode);
+void set_inverse_window(int w);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
 void set_sds_literal(int v);       // 1: R = K - V^T V as the reference writes it (parity), 0: reduced form (default)
 void set_sds_runahead(int r);      // rounds queued ahead of the last status word seen (0: auto)
 void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);

@@ -35,6 +35,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &p, int m, int tm, 
             if (p.epi == EPI_SUB) {
                 if (two) { const double2 c = *reinterpret_cast<const double2 *>(crow + cl); v0 = c.x - v0; v1 = c.y - v1; }
                 else v0 = crow[cl] - v0;
+            } else if (p.epi == EPI_ADD) {
+                if (two) { const double2 c = *reinterpret_cast<const double2 *>(crow + cl); v0 = c.x + v0; v1 = c.y + v1; }
+                else v0 = crow[cl] + v0;
             } else if (p.epi == EPI_NEGSET) {
                 v0 = -v0; v1 = -v1;
             } else if (p.epi == EPI_R) {

@@ -113,7 +113,7 @@ gemm_dmma_tma_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tmA, const 
     // the epilogue subtracts from the C tile: ask L2 for its 512 lines now (two per thread), so that the loads at the
     // end of the K loop do not wait for HBM -- matters for the short contractions only (K = 128 parts of the look-ahead,
     // N = 512 matrices: +1 ... 1.5 %; long contractions hide the epilogue behind the co-resident CTA anyway)
-    if (p.epi == EPI_SUB && klen <= 512) {
+    if ((p.epi == EPI_SUB || p.epi == EPI_ADD) && klen <= 512) {
         const double *Cb = p.C.base + (size_t)m * p.C.stride + (size_t)(p.cr0 + tm * TBM) * p.C.ld + p.cc0 + tn * TBN;
 #pragma unroll
         for (int e = tid; e < TBM * (TBN / 16); e += TTHREADS) {
@@ -382,7 +382,7 @@ gemm_dmma_tma_persistent_kernel(GemmArgs p, const __grid_constant__ CUtensorMap 
         }
 
         const int m = cur.m, tm = cur.tm, tn = cur.tn, rows_valid = cur.rows_valid, cols_valid = cur.cols_valid, nk = cur.nk;
-        if (p.epi == EPI_SUB && cur.klen <= 512) {
+        if ((p.epi == EPI_SUB || p.epi == EPI_ADD) && cur.klen <= 512) {
             const double *Cb = p.C.base + (size_t)m * p.C.stride + (size_t)(p.cr0 + tm * TBM) * p.C.ld + p.cc0 + tn * TBN;
 #pragma unroll
             for (int e = tid; e < TBM * (TBN / 16); e += TTHREADS) {

@@ -449,6 +449,85 @@ int border_finish(BatchView A, int n, double *loglik, const int *info, int B, cu
 // U = L^-T, built block column by block column in the upper triangle of the same buffer:
 //   U[0:i0, i] = -(U[0:i0, 0:i0] L[i, 0:i0]^T) (L_ii^-1)^T ,   U[i, i] = (L_ii^-1)^T
 // (the k < row part of U is zero, so every tile starts its contraction at its own first row).
+// Window of the triangular inverse (0 = none).  The plain sequence computes block column i of U = L^-T as
+// Y_i = U[0:i0, 0:i0] L[i, 0:i0]^T (one launch of i0/128 x 2 tiles per matrix, contraction up to i0) and multiplies by
+// -W_i^T: with few matrices in flight every one of those launches is a fraction of a wave of long-K tiles (measured: 0.30
+// of DGEMM for 2-3 matrices of 8192, profiles/r02r_large_n_sds.json).  Windowed: the strict upper triangle is zeroed and
+// serves as the accumulator of Y; inside a window the contraction is limited to the window's own columns, and after a
+// window ONE launch adds its contribution to every later block column,  Y[0:w1, w1:n] += U[0:w1, w0:w1] L[w1:n, w0:w1]^T
+// -- thousands of tiles with K = window, like the trailing update of the windowed Cholesky.
+static int g_inverse_window = -1;      // -1 auto, 0 off, else forced (multiple of 128)
+void set_inverse_window(int w) { g_inverse_window = (w >= 0 && w % NB == 0) ? w : -1; }
+
+static int inverse_window_for(int n, int B)
+{
+    int w = g_inverse_window;
+    if (w < 0) {
+        const int nt = (n + NB - 1) / NB;
+        w = (long long)B * nt >= 1024 ? 0 : (n >= 8192 ? 1024 : 512);
+    }
+    return (w > 0 && w < n) ? w : 0;
+}
+
+static int inverse_sequence_windowed(BatchView A, int n, int B, const double *W, long long strideW, int window, cudaStream_t s)
+{
+    const Operand self{A.base, A.stride, A.ld};
+    int rc = zero_upper(A, n, B, s);                    // Y accumulates in the strict upper triangle
+    if (rc) return rc;
+    // The product that follows a window is split like the trailing update of the windowed Cholesky: the NEXT window's
+    // columns first (its block columns wait for them), the columns beyond on the caller's stream while the next window's
+    // chain of small launches runs on the high-priority side stream.  Events only; the caller's stream joins at the end.
+    LookAhead *la = lookahead_ctx();
+    const cudaStream_t sC = la ? la->panel : s;         // chain: in-window products, panel multiplies, diagonal blocks, near parts
+    const cudaStream_t sF = s;                          // far parts
+    if (la) {
+        GPMC_CUDA_CHECK(cudaEventRecord(la->ev_a, s));
+        GPMC_CUDA_CHECK(cudaStreamWaitEvent(sC, la->ev_a, 0));
+    }
+    bool far_pending = false;
+    auto add_product = [&](int rows, int c0, int cols, int k_begin, int k_end, cudaStream_t st) -> int {
+        // Y[0:rows, c0:c0+cols] += U[0:rows, k_begin:k_end] L[c0:c0+cols, k_begin:k_end]^T   (U upper triangular: rows below k skip)
+        GemmArgs g{};
+        g.C = A; g.A = self; g.B = self;
+        g.cr0 = 0; g.cc0 = c0; g.rows = rows; g.cols = cols;
+        g.ar0 = 0; g.br0 = c0; g.k0 = k_begin; g.bk0 = k_begin; g.klen = k_end - k_begin;
+        g.k_follow_row = 1;
+        g.epi = EPI_ADD;
+        return launch_gemm(g, B, KC_INV, st);
+    };
+    for (int w0 = 0; w0 < n; w0 += window) {
+        const int w1 = std::min(n, w0 + window);
+        for (int i0 = w0; i0 < w1; i0 += NB) {
+            const int width = std::min(NB, n - i0);
+            const double *Wi = W + (size_t)(i0 / NB) * NB * NB;
+            if (i0 > 0) {
+                if (i0 > w0 && (rc = add_product(i0, i0, width, w0, i0, sC))) return rc;
+                // U[0:i0, i] = -(Y W_i^T), in place
+                if ((rc = launch_trmm_panel8(A, i0, i0, width, Wi, strideW, B, sC))) return rc;
+            }
+            prof_begin(KC_INV, sC);
+            write_diag_block_T_kernel<<<B, 256, 0, sC>>>(A, n, i0, Wi, strideW);
+            prof_end(KC_INV, sC);
+            GPMC_LAUNCH_CHECK();
+        }
+        if (w1 >= n) break;
+        const int w2 = std::min(n, w1 + window);
+        if (la) GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sC));                       // this window's columns of U are final
+        if (la && far_pending) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sC, la->ev_q, 0)); // the near part adds on top of the last far part
+        if ((rc = add_product(w1, w1, w2 - w1, w0, w1, sC))) return rc;               // near: the next window's columns
+        if (w2 < n) {
+            if (la) GPMC_CUDA_CHECK(cudaStreamWaitEvent(sF, la->ev_p, 0));
+            if ((rc = add_product(w1, w2, n - w2, w0, w1, sF))) return rc;            // far: everything beyond
+            if (la) { GPMC_CUDA_CHECK(cudaEventRecord(la->ev_q, sF)); far_pending = true; }
+        }
+    }
+    if (la) {                                           // join
+        GPMC_CUDA_CHECK(cudaEventRecord(la->ev_p, sC));
+        GPMC_CUDA_CHECK(cudaStreamWaitEvent(s, la->ev_p, 0));
+    }
+    return 0;
+}
+
 int inverse_sequence(BatchView A, int n, int B, const double *W, long long strideW, cudaStream_t s)
 {
     const int nt = (n + NB - 1) / NB;
@@ -458,6 +537,7 @@ int inverse_sequence(BatchView A, int n, int B, const double *W, long long strid
         int rc = launch_inv_blocks8(A, n, const_cast<double *>(W), strideW, B, s);
         if (rc) return rc;
     }
+    if (const int window = inverse_window_for(n, B)) return inverse_sequence_windowed(A, n, B, W, strideW, window, s);
     for (int i = 0; i < nt; ++i) {
         const int i0 = i * NB;
         const int width = std::min(NB, n - i0);

@@ -256,7 +256,9 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  *        flight), 1 = never, 2 = whenever the default panel kernels are selected.
  * key 10: in-window update of a look-ahead column: 0 = auto (split in a long and a K = 128 short part when a trailing update
  *        runs beside the window or the launches are small; one launch otherwise), 1 = always split, 2 = one launch in every
- *        window that runs alone. */
+ *        window that runs alone.
+ * key 11: window (columns, multiple of 128) of the triangular inverse U = L^-T: -1 = auto (windows of 512 / 1024 columns when
+ *        few matrices are in flight), 0 = none (one long-K product per block column), else forced. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:

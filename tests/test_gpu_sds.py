@@ -534,3 +534,61 @@ def test_checkpoint_resume_continues_bit_for_bit(gp, tmp_path):
     assert np.array_equal(np.concatenate([h1, h2], axis=2), hist)
     assert np.array_equal(np.concatenate([l1, l2], axis=1), ll) and np.array_equal(np.concatenate([t1, t2], axis=1), trips)
     assert np.array_equal(res.local_state()[0], full.local_state()[0])
+
+
+@pytest.mark.parametrize('n,window', [(700, 256), (1100, 512), (900, 128)])
+def test_windowed_triangular_inverse_matches_plain_and_oracle(gp, n, window):
+    """inverse_sequence_windowed (sequences.cu; tuning key 11): Y accumulated in the zeroed upper triangle window by window
+    (EPI_ADD) instead of one long-K product per block column -- the schedule for few large matrices.  Through the
+    single-matrix auxiliary model: m and C = chol(R + 1e-11 I) must agree with the plain sequence to rounding and with
+    the oracle's reduced form."""
+    import torch
+    from oracle import sds_oracle as so
+    x, y = gp.synthetic.ih45_series(n)
+    hyp = np.array([3.0, 6.0, 1.3])
+    K = so.cov_matrix(np.asarray(x, dtype=np.float64).reshape(n, -1), hyp)
+    S = so.s_diagonal(np.diagonal(K), hyp[-1])
+    g = 0.4 * (y - y.mean()) + np.random.RandomState(n).standard_normal(n) * np.sqrt(S)
+    out = {}
+    try:
+        for w in (0, window):
+            gp.ops.set_tuning(11, w)
+            L, m, C, info = gp.ops.aux_var_model_device(torch.tensor(K).cuda(), torch.tensor(S).cuda(), torch.tensor(g).cuda())
+            assert int(info.abs().sum().item()) == 0
+            out[w] = (m.cpu().numpy(), C.cpu().numpy())
+    finally:
+        gp.ops.set_tuning(11, -1)
+    m0, C0 = out[0]
+    m1, C1 = out[window]
+    R0, R1 = C0 @ C0.T, C1 @ C1.T
+    assert np.abs(R1 - R0).max() <= 1e-12 * np.abs(R0).max()
+    np.testing.assert_allclose(m1, m0, rtol=1e-9, atol=1e-11 * np.abs(m0).max())
+    # oracle: R = S - S (K+S)^-1 S, m = R S^-1 g
+    KS = K + np.diag(S)
+    Ro = np.diag(S) - (S[:, None] * np.linalg.solve(KS, np.diag(S)))
+    mo = Ro @ (g / S)
+    assert np.abs(R1 - 1e-11 * np.eye(n) - Ro).max() <= 1e-9 * np.abs(Ro).max()
+    np.testing.assert_allclose(m1, mo, rtol=1e-7, atol=1e-9 * np.abs(mo).max())
+
+
+def test_windowed_inverse_inside_the_sds_sweep(gp):
+    """A whole transition with the windowed inverse forced (window 128 at N=300: three windows) takes the same decisions
+    as with the plain sequence and matches it to rounding."""
+    import torch
+    n, B = 300, 5
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array([10., 10., 5.])
+    out = {}
+    try:
+        for w in (0, 128):
+            gp.ops.set_tuning(11, w)
+            F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+            trips, ll, status = gp.ops.sds_sweep(x, y, F, H, scale, 2, seed=11)
+            out[w] = (trips.cpu().numpy(), H.cpu().numpy(), F.cpu().numpy(), ll.cpu().numpy())
+    finally:
+        gp.ops.set_tuning(11, -1)
+    assert np.array_equal(out[0][0], out[128][0])
+    np.testing.assert_allclose(out[128][1], out[0][1], rtol=1e-12)
+    np.testing.assert_allclose(out[128][3], out[0][3], rtol=1e-10)
+    np.testing.assert_allclose(out[128][2], out[0][2], rtol=0, atol=1e-6 * np.abs(out[0][2]).max())
