@@ -259,7 +259,6 @@ def sub_loglik(gp, torch, np, name, n, B, ard, reps, peak_tf, n_check, what):
     for _ in range(3):
         ll, info = gp.ops.loglik_batched(xd, Gd, Hd)
     torch.cuda.synchronize()
-    gp.ops.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -267,6 +266,13 @@ def sub_loglik(gp, torch, np, name, n, B, ard, reps, peak_tf, n_check, what):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    # per-class kernel times from a separate pass: the event pairs around every launch cost 3-4 % on the look-ahead
+    # schedules (hundreds of launches on three streams), so they stay out of the timed region
+    preps = max(1, min(reps, 3))
+    gp.ops.profile(True)
+    for _ in range(preps):
+        gp.ops.loglik_batched(xd, Gd, Hd)
+    torch.cuda.synchronize()
     prof = gp.ops.profile_read()
     gp.ops.profile(False)
     launches = int(sum(v[1] for v in prof.values()))
@@ -283,8 +289,9 @@ def sub_loglik(gp, torch, np, name, n, B, ard, reps, peak_tf, n_check, what):
            'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'flop_per_eval': n ** 3 / 3.0,
                         'achieved': tf_pass, 'peak': peak_tf, 'frac': tf_pass / peak_tf if peak_tf else None,
                         'what': 'N^3/3 flop per eval over the WALL time of the whole pass (assembly, reductions, launch gaps included)'},
-           'kernel_ms': {k: round(v[0] / reps, 4) for k, v in prof.items() if v[0] > 0},
-           'gpu_launches_per_pass': launches // max(1, reps),
+           'kernel_ms': {k: round(v[0] / preps, 4) for k, v in prof.items() if v[0] > 0},
+           'kernel_ms_note': 'from a separate pass with CUDA event pairs around every launch (not the timed passes)',
+           'gpu_launches_per_pass': launches // preps,
            'gpu_vs_oracle_max_rel_err': rel, 'oracle_items': [int(i) for i in idx],
            'cpu_oracle_s_per_eval': cpu_dt / len(idx)}
     del xd, Gd, Hd
@@ -306,31 +313,45 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     P = n_ell + 2
     scale = np.array([gp.synthetic.SCALE[0]] * n_ell + list(gp.synthetic.SCALE[1:]))
     F0, H0 = gp.synthetic.chain_states(B, n, n_ell=n_ell, first_chain=rank * B)
-    ens = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=1, max_trips=64, sharded_input=True,
-                                  distributed=(world > 1))
-    ens.sweep(start_iter)                                   # warm-up: allocations, lazy module load, NCCL
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    gp.ops.profile(True)
-    busy, trips = [], []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    if run_mode:
-        # the whole caller loop in ONE device call (gpmc_sds_run): chains advance on their own, one all-gather at the end
-        _, _, ntg = ens.run(sweeps, start_iter=start_iter + 1)
-        busy.append(ens.last_busy_ms)
-        trips = [ntg[:, i] for i in range(sweeps)]
-    else:
-        for i in range(sweeps):
-            Hg, llg, ntg = ens.sweep(start_iter + 1 + i)    # gathered over ranks
+
+    def one_pass(profile):
+        """The same sweeps from the same state and seeds (identical work); with `profile` every launch is bracketed by a
+        CUDA event pair -- thousands of them, so the per-class kernel times come from a pass of their own, not the timed one."""
+        ens = gp.chains.ChainEnsemble(x, y, F0, H0, scale, seed=1, max_trips=64, sharded_input=True,
+                                      distributed=(world > 1))
+        ens.sweep(start_iter)                                   # warm-up: allocations, lazy module load, NCCL
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if profile:
+            gp.ops.profile(True)
+        busy, trips = [], []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if run_mode:
+            # the whole caller loop in ONE device call (gpmc_sds_run): chains advance on their own, one all-gather at the end
+            _, _, ntg = ens.run(sweeps, start_iter=start_iter + 1)
             busy.append(ens.last_busy_ms)
-            trips.append(ntg)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    prof = gp.ops.profile_read()
-    gp.ops.profile(False)
+            trips = [ntg[:, i] for i in range(sweeps)]
+        else:
+            for i in range(sweeps):
+                Hg, llg, ntg = ens.sweep(start_iter + 1 + i)    # gathered over ranks
+                busy.append(ens.last_busy_ms)
+                trips.append(ntg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        prof = gp.ops.profile_read() if profile else None
+        if profile:
+            gp.ops.profile(False)
+        return ms, busy, trips, prof, ens
+
+    ms, busy, trips, _, ens = one_pass(False)
+    exhausted_total = int(ens.exhausted_total)
+    del ens
+    _, _, trips_p, prof, ens = one_pass(True)
+    assert all(np.array_equal(a_, b_) for a_, b_ in zip(trips, trips_p)), 'the profiled pass did not repeat the timed one'
+    del ens
     busy_local = float(np.sum(busy))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
@@ -350,7 +371,7 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
            'ard_dims': ard, 'sweeps': sweeps, 'start_iter': start_iter + 1,
            's_per_sweep': ms * 1e-3 / sweeps, 'chain_sweeps_per_s': world * B * sweeps / (ms * 1e-3),
            'mean_trips': float(trips.mean()), 'max_trips': int(trips.max()), 'aux_evals': evals,
-           'exhausted_chains': int(ens.exhausted_total),
+           'exhausted_chains': exhausted_total,
            'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'flop_per_aux_eval': (4.0 / 3.0) * n ** 3,
                         'achieved': tf, 'peak': peak_tf * world if peak_tf else None,
                         'frac': tf / (peak_tf * world) if peak_tf else None,
@@ -359,8 +380,8 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
            'busy_ms_per_rank': busy_ranks,
            'imbalance_max_over_mean': (max(busy_ranks) / (sum(busy_ranks) / len(busy_ranks))) if min(busy_ranks) > 0 else None,
            'kernel_ms_rank0': {k: round(v[0], 3) for k, v in prof.items() if v[0] > 0},
+           'kernel_ms_note': 'from a repeat of the same sweeps with CUDA event pairs around every launch (not the timed pass)',
            'gpu_launches_rank0': int(sum(v[1] for v in prof.values()))}
-    del ens
     # ---- parity on sampled chains: tape-driven transition on the device vs the tape-driven oracle (reduced R form, the
     # one the device evaluates): theta' and trip counts exact, log N(g) to 1e-10
     if rank == 0 and n_check > 0:
