@@ -184,7 +184,8 @@ static int potrf_window_for(int n, int B)
     // plain left-looking once the launches fill the chip several times over -- unless the look-ahead schedule is on anyway
     // (at most #SMs/2 matrices): there windows of 512 measured 3.5 % faster than none at N=2048 x 64 (tools/window_c2.py)
     if ((long long)B * nt >= 1024 && 2 * B > sm_count()) return 0;
-    return n >= 8192 ? 1024 : 512;
+    // (N=8192 x 1: 8.58 / 8.65 / 9.00 / 10.4 ms with windows of 256 / 512 / 1024 / 2048 columns; N=16384 x 1 does not care)
+    return n >= 12288 ? 1024 : 512;
 }
 
 static int g_trsm_mode = 0;
