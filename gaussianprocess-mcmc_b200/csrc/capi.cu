@@ -421,6 +421,7 @@ int gpmc_set_tuning(int key, int value)
     if (key == 9) { set_panel_fuse(value); return 0; }
     if (key == 10) { set_lookahead_split(value); return 0; }
     if (key == 11) { set_inverse_window(value); return 0; }
+    if (key == 13) { set_sds_pin_schedule(value); return 0; }
     return GPMC_EINVAL;
 }
 

@@ -178,6 +178,7 @@ void set_lookahead_split(int mode);
 void set_inverse_window(int w);     // fused panel factor + solve launches: 0 auto (many small matrices), 1 never, 2 whenever possible
 void set_sds_literal(int v);       // 1: R = K - V^T V as the reference writes it (parity), 0: reduced form (default)
 void set_sds_runahead(int r);      // rounds queued ahead of the last status word seen (0: auto)
+void set_sds_pin_schedule(int v);  // 1: factorisation schedules of the resident loop chosen from a constant (bit-reproducible runs)
 void sds_loop_stats(long long *rounds, long long *idle_rounds, long long *ladders);
 
 // microbench.cu

@@ -174,6 +174,13 @@ static int sm_count()
     return sms;
 }
 
+// The schedules below are chosen from the number of matrices in the launch.  A caller whose launch sizes are only upper
+// bounds that move with timing (the resident SDS loop in the tail of a call) pins the number the CHOICE is made from, so that
+// the summation order -- and with it every bit of the result -- repeats from run to run.
+static int g_schedule_batch = 0;       // 0: choose from the launch's own B
+void set_schedule_batch(int B) { g_schedule_batch = B > 0 ? B : 0; }
+static int schedule_batch(int B) { return g_schedule_batch > 0 ? g_schedule_batch : B; }
+
 static int g_window_override = 0;
 void set_potrf_window(int w) { g_window_override = (w > 0 && w % NB == 0) ? w : 0; }
 
@@ -247,6 +254,7 @@ void set_panel_fuse(int mode) { g_panel_fuse = mode; }
 // into different phases.  With few or large matrices the solve needs many CTAs per matrix: separate launches.
 int potrf_fuse_auto(int n, int B, int border_rows)
 {
+    B = schedule_batch(B);
     if (!lite_panels() || (g_potf2_mode != 0 && g_potf2_mode != 3) || g_panel_fuse == 1) return 0;
     if (g_panel_fuse == 2) return 1;
     // many small matrices (co-resident CTAs drift into different phases), or any number of very small ones (two launches
@@ -270,11 +278,12 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
     // Measured: it is the faster of the two at every batch size.  Callers that keep the block inverses (w_step != 0)
     // get them completed by inverse_sequence (launch_inv_blocks8) from those 8x8 blocks.
     const bool lite = lite_panels();
-    const int window = potrf_window_for(n, B);
+    const int Bs = schedule_batch(B);                   // what the schedule is chosen from (launch sizes keep using B)
+    const int window = potrf_window_for(n, Bs);
     const Operand self{A.base, A.stride, A.ld};
     const int wlen = window > 0 ? window : n;
     LookAhead *la = nullptr;
-    if (!fuse && n > 2 * NB && (g_lookahead_mode == 2 || (g_lookahead_mode == 0 && 2 * B <= sm_count()))) la = lookahead_ctx();
+    if (!fuse && n > 2 * NB && (g_lookahead_mode == 2 || (g_lookahead_mode == 0 && 2 * Bs <= sm_count()))) la = lookahead_ctx();
     // streams: trailing updates / in-window updates / panel kernels
     const cudaStream_t sG = s;
     const cudaStream_t sQ = la ? (window > 0 ? la->inwin : s) : s;
@@ -327,7 +336,7 @@ int potrf_sequence(BatchView A, int n, int B, int *info, double *W, long long st
         // when their launches fill the chip several times over anyway, the two K-short launches (23 TFLOP/s at K = 128)
         // cost more than the 35 us of an exposed panel factor kernel (tools/timeline.py).
         const bool paired = w0 > 0 && w1 < n;
-        const bool many_ctas = (long long)B * ((n - w0 + 127) / 128) * 2 >= 8LL * sm_count();
+        const bool many_ctas = (long long)Bs * ((n - w0 + 127) / 128) * 2 >= 8LL * sm_count();
         const bool split_cols = la && (g_split_mode == 1 || paired || (g_split_mode == 0 && !many_ctas));
         for (int j0 = w0; j0 < w1; j0 += NB) {
             const int width = std::min(NB, n - j0);
@@ -538,7 +547,7 @@ int inverse_sequence(BatchView A, int n, int B, const double *W, long long strid
         int rc = launch_inv_blocks8(A, n, const_cast<double *>(W), strideW, B, s);
         if (rc) return rc;
     }
-    if (const int window = inverse_window_for(n, B)) return inverse_sequence_windowed(A, n, B, W, strideW, window, s);
+    if (const int window = inverse_window_for(n, schedule_batch(B))) return inverse_sequence_windowed(A, n, B, W, strideW, window, s);
     for (int i = 0; i < nt; ++i) {
         const int i0 = i * NB;
         const int width = std::min(NB, n - i0);

@@ -39,6 +39,8 @@ int border_get(BatchView A, int n, double *z, int ldv, const int *info, int B, c
 // In place L (lower) -> U = L^-T (upper triangle incl. diagonal blocks; the strict lower block part keeps L).
 // Needs the saved diagonal-block inverses of potrf_sequence (w_step = NB*NB).
 int inverse_sequence(BatchView A, int n, int B, const double *W, long long strideW, cudaStream_t s);
+// pin the batch size the schedules are CHOSEN from (0 = each launch's own): see sequences.cu
+void set_schedule_batch(int B);
 
 // R = S - S (U U^T) S + 1e-11 I, lower tiles only, from U (upper, in A) into Rm.  svec = diag(S) per item.
 int r_sequence(BatchView Rm, BatchView U, int n, int B, const double *svec, long long stride_s, cudaStream_t s);

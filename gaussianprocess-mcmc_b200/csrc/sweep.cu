@@ -40,6 +40,8 @@ struct SweepBuffers {
 };
 
 // R = K - V^T V (sliceSample.py:197-198) formed as the reference writes it (gpmc_set_tuning(8, 1)) instead of the reduced form
+static int g_sds_pin_schedule = 0;     // tuning key 13
+void set_sds_pin_schedule(int v) { g_sds_pin_schedule = v ? 1 : 0; }
 static int g_sds_literal = 0;
 void set_sds_literal(int v) { g_sds_literal = v ? 1 : 0; }
 
@@ -461,6 +463,14 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
     ResidentHost *rh = resident_host();
     if (!rh) { set_error("sds_sweep: cannot allocate the pinned status ring"); return GPMC_ENOMEM; }
     const int cap = w.cap;
+    // Launch sizes follow the polled status words in the tail of the call, and the factorisation schedules are chosen from
+    // them (few matrices left: look-ahead, windows).  With tuning key 13 the choice is made from this constant instead: the
+    // summation order, and so every bit of the result, is then independent of the host's timing, at 1-4 % of the sweep
+    // (N=4096 x 256: 2.59 -> 2.69 s).  N <= 512 has a single schedule and repeats exactly either way.
+    struct SchedulePin {
+        explicit SchedulePin(int B) { set_schedule_batch(B); }
+        ~SchedulePin() { set_schedule_batch(0); }
+    } pin(g_sds_pin_schedule ? std::min(cap, B) : 0);
     AuxCtx ctx{x_dev, N, D, P, n_ell, &w, s, jitter_policy};
     int rc;
     // every slot free, nothing admitted yet

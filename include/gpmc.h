@@ -258,7 +258,10 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  *        runs beside the window or the launches are small; one launch otherwise), 1 = always split, 2 = one launch in every
  *        window that runs alone.
  * key 11: window (columns, multiple of 128) of the triangular inverse U = L^-T: -1 = auto (windows of 512 / 1024 columns when
- *        few matrices are in flight), 0 = none (one long-K product per block column), else forced. */
+ *        few matrices are in flight), 0 = none (one long-K product per block column), else forced.
+ * key 13: 1 = the resident SDS loop chooses its factorisation schedules from a constant (min(slots, chains)) instead of the
+ *        launch sizes, which in the tail of a call follow the polled status words: results then repeat bit for bit from run
+ *        to run for every N (N <= 512 always does), at 1-4 % of the sweep time.  0 = default. */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:
