@@ -517,12 +517,12 @@ static int sds_sweep_resident(const double *x_dev, const double *y_dev, int N, i
     int known_next = 0, known_count = cap, known_parked = 0;
     bool finished = false;
     long long round = 0, polled = 0;            // rounds queued / status words consumed
-    // run-ahead: deep enough that the device never waits for the host, shallow enough that the idle rounds queued past the
-    // end cost little next to a round of real work
-    const double round_flops = (double)std::min(cap, B) * (4.0 / 3.0) * (double)N * N * N;
-    // (a single small chain: a round is ~60 launches of a few microseconds each, an idle round costs as much as a real one,
-    //  so the host waits for every status word there -- run-ahead 1)
-    int runahead = g_sds_runahead > 0 ? g_sds_runahead : (round_flops > 2e11 ? 4 : (round_flops > 2e10 ? 3 : (round_flops > 1e9 ? 2 : 1)));
+    // Run-ahead: ONE round.  The host sizes round r from the status word of round r-1's admission -- a word that is ready
+    // early in round r-1, so the host still queues a whole round ahead of the device -- and it reads EVERY word before it
+    // sizes the next round (the blocking wait below), so launch sizes, schedules and results do not depend on its timing.
+    // Deeper run-ahead (tuning key 7) sizes rounds from older, larger bounds and queues idle rounds past the end of the
+    // call: measured 1.4-4 % slower at N=1024 ... 4096 (and no faster anywhere), and no longer repeatable bit for bit.
+    int runahead = g_sds_runahead > 0 ? g_sds_runahead : 1;
     runahead = std::min(runahead, ResidentHost::RING - 1);
     g_sds_rounds = g_sds_idle_rounds = g_sds_ladders = 0;
 

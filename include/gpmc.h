@@ -247,7 +247,8 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  * key 5: 64-row blocks one CTA of the panel solve takes: 0 = auto (1, 2 or 4 by launch size), else forced.
  * key 6: gpmc_sds_sweep loop: 0 = resident loop (slots refilled on the device, host polls a status word without
  *        synchronising; default), 1 = wave loop (one status read per trip, waves drained to their slowest chain).
- * key 7: rounds the resident loop queues ahead of the last status word it has seen (0 = auto: 2..4 by problem size).
+ * key 7: rounds the resident loop queues ahead of the last status word it has seen (0 = default: 1, every status word is
+ *        read before the next round is sized: launch sizes and results independent of host timing; 2..7: deeper, polled).
  * key 8: form of the posterior covariance inside gpmc_sds_sweep / gpmc_sds_run: 0 = reduced, R = S - S (K+S)^-1 S (4/3 N^3
  *        flop per evaluation; default), 1 = literal, V = solve(L, K), R = K - V^T V, m = (R inv(S)) g exactly as
  *        sliceSample.py:197-198,204 write it (8/3 N^3; twice the workspace per chain -- query gpmc_sds_workspace_bytes
@@ -260,8 +261,8 @@ int gpmc_ess_sweep(const double *x_dev, const double *y_dev, int N, int D, doubl
  * key 11: window (columns, multiple of 128) of the triangular inverse U = L^-T: -1 = auto (windows of 512 / 1024 columns when
  *        few matrices are in flight), 0 = none (one long-K product per block column), else forced.
  * key 13: 1 = the resident SDS loop chooses its factorisation schedules from a constant (min(slots, chains)) instead of the
- *        launch sizes, which in the tail of a call follow the polled status words: results then repeat bit for bit from run
- *        to run for every N (N <= 512 always does), at 1-4 % of the sweep time.  0 = default. */
+ *        launch sizes: with a run-ahead deeper than 1 (key 7) those follow polled status words, and this keeps results
+ *        repeatable bit for bit beyond N = 512 (1-4 % of the sweep time).  0 = default (not needed at run-ahead 1). */
 int gpmc_set_tuning(int key, int value);
 
 /* FP64 micro-benchmarks used by bench.py to put a measured peak beside the roofline:

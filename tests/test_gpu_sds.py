@@ -596,8 +596,8 @@ def test_windowed_inverse_inside_the_sds_sweep(gp):
 
 def test_pinned_schedule_repeats_bit_for_bit(gp):
     """N = 700 (several schedules exist: windows, look-ahead, fused panels by batch size) with more chains than slots, so the
-    tail of the call runs on polled launch sizes: with tuning key 13 the schedules are chosen from a constant and three
-    runs give identical bits; decisions agree with the default mode."""
+    tail of the call runs on polled launch sizes when the run-ahead is deeper than one round (key 7): with tuning key 13 the
+    schedules are chosen from a constant and three runs give identical bits; decisions agree with the default mode."""
     import torch
     n, B = 700, 7
     x, y = gp.synthetic.ih45_series(n)
@@ -611,13 +611,36 @@ def test_pinned_schedule_repeats_bit_for_bit(gp):
 
     base = run()
     try:
+        gp.ops.set_tuning(7, 4)           # deep run-ahead: launch sizes follow non-blocking polls of the status ring
         gp.ops.set_tuning(13, 1)
         runs = [run() for _ in range(3)]
     finally:
         gp.ops.set_tuning(13, 0)
+        gp.ops.set_tuning(7, 0)
     for r in runs[1:]:
         for a, b in zip(runs[0], r):
             assert np.array_equal(a, b)
     assert np.array_equal(runs[0][0], base[0])
     np.testing.assert_allclose(runs[0][1], base[1], rtol=1e-12)
     np.testing.assert_allclose(runs[0][3], base[3], rtol=1e-10)
+
+
+def test_large_n_resident_loop_repeats_bit_for_bit_by_default(gp):
+    """Beyond N = 512 the factorisation schedules depend on the launch sizes; the resident loop then queues exactly one
+    round ahead and reads every status word before it sizes the next round, so its launch sizes -- and the bits of the
+    result -- do not depend on the host's timing.  More chains than slots: the tail of the call runs on shrinking counts."""
+    import torch
+    n, B = 700, 7
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array([10., 10., 5.])
+
+    def run():
+        F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+        trips, ll, status = gp.ops.sds_sweep(x, y, F, H, scale, 2, seed=17, chains_per_wave=3)
+        return trips.cpu().numpy(), H.cpu().numpy(), F.cpu().numpy(), ll.cpu().numpy()
+
+    runs = [run() for _ in range(4)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert np.array_equal(a, b)
