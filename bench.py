@@ -412,6 +412,86 @@ def sub_sds(gp, torch, np, name, n, B, ard, sweeps, start_iter, peak_tf, n_check
     return rec
 
 
+def sub_predict(gp, torch, np, n=455, S=100, M=40, reps=5, n_check=3):
+    """`inf_mcmc` (sliceSample.py:234-284) for S stored samples in ONE device pass (gpmc_predict_batched) --
+    the call crossValid.execute makes per fold (framework.py:223-243), IH45-sized series -- against the oracle's per-sample
+    restatement timed on the host."""
+    from oracle import sds_oracle as so
+    rs = np.random.RandomState(77)
+    x, y = gp.synthetic.ih45_series(n)
+    xs = np.sort(rs.uniform(0, n, size=(M, 1)), axis=0)
+    Hyp = np.column_stack([rs.uniform(1.5, 7., S), rs.uniform(2., 9., S), rs.uniform(0.6, 2.8, S)])
+    F = (y - y.mean())[:, None] * 0.7 + 0.3 * rs.standard_normal((n, S))
+    Ft = np.ascontiguousarray(F.T)
+    xd, xsd = torch.tensor(np.asarray(x, dtype=np.float64).reshape(n, -1)).cuda(), torch.tensor(xs).cuda()
+    Fd, Hd = torch.tensor(Ft).cuda(), torch.tensor(Hyp).cuda()
+    for _ in range(2):
+        fmu, fs2, info = gp.ops.predict_batched(xd, xsd, Fd, Hd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fmu, fs2, info = gp.ops.predict_batched(xd, xsd, Fd, Hd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fmu_h, fs2_h = fmu.cpu().numpy(), fs2.cpu().numpy()
+    worst_mu = worst_s2 = 0.0
+    t0 = time.perf_counter()
+    for s_ in range(n_check):
+        _, _, _, Fs2, Fmu = so.inf_mcmc_unit(F[:, s_], x, y, xs, Hyp[s_])
+        worst_mu = max(worst_mu, float(np.max(np.abs(fmu_h[s_] - Fmu[:, 0]) / np.maximum(np.abs(Fmu[:, 0]), 1e-9))))
+        worst_s2 = max(worst_s2, float(np.max(np.abs(np.maximum(fs2_h[s_], 0) - Fs2[:, 0]) / np.maximum(np.abs(Fs2[:, 0]), 1e-10))))
+    cpu = (time.perf_counter() - t0) / n_check
+    return {'name': 'F2_predict', 'kind': 'predict', 'workload': 'SURVEY row f2: inf_mcmc for %d stored samples x %d test points at N=%d in one '
+            'gpmc_predict_batched call (right-hand sides as border rows of the factorisation)' % (S, M, n),
+            'n': n, 'samples': S, 'test_points': M, 'reps': reps, 'ms_per_call': ms, 'samples_per_s': S / (ms * 1e-3),
+            'failed_items': int((info != 0).sum().item()),
+            'gpu_vs_oracle': {'samples': n_check, 'fmu_max_rel_err': worst_mu, 'fs2_max_rel_err': worst_s2, 'cpu_oracle_s_per_sample': cpu}}
+
+
+def sub_ess(gp, torch, np, n=455, B=1024, updates=5, n_check=2):
+    """`elliptical_slice` (sliceSample.py:15-74) as a device path (gpmc_ess_sweep: nu = chol(K) z and the
+    whole bracket loop per chain), B chains with their own hyper-parameters; tape-driven check against the oracle."""
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import EssTape
+    rs = np.random.RandomState(78)
+    x, y = gp.synthetic.ih45_series(n)
+    Hyp = np.column_stack([rs.uniform(2., 6., B), rs.uniform(3., 8., B), rs.uniform(0.8, 2.5, B)])
+    F0 = np.tile(0.7 * (y - y.mean()), (B, 1))
+    F, Hd = torch.tensor(F0).cuda(), torch.tensor(Hyp).cuda()
+    gp.ops.ess_sweep(x, y, F, Hd, it=0, seed=5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trips = 0.0
+    e0.record()
+    for it in range(updates):
+        nt, st, info = gp.ops.ess_sweep(x, y, F, Hd, it=1 + it, seed=5)
+        trips += float(nt.double().mean().item())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / updates
+    # tape-driven: the N(0, K) draw nu on the tape, decisions and f' against the oracle
+    worst = 0.0
+    trips_equal = True
+    t0 = time.perf_counter()
+    for c in range(n_check):
+        r2 = np.random.RandomState(900 + c)
+        nu = so.ess_nu_from_z(x, Hyp[c], r2.standard_normal(n))
+        u, th = r2.random_sample(), r2.random_sample(64)
+        of, ot = so.elliptical_slice(F0[c], x, y, Hyp[c], EssTape(nu, u, th))
+        Fc = torch.tensor(F0[c][None].copy()).cuda()
+        ntc, stc, _ = gp.ops.ess_sweep(x, y, Fc, Hyp[c][None], tape=gp.ops.EssTape([float(u)], th[None], nu=nu[None]), max_trips=64)
+        trips_equal = trips_equal and int(ntc.item()) == ot
+        worst = max(worst, float(np.abs(Fc.cpu().numpy()[0] - of).max()))
+    cpu = (time.perf_counter() - t0) / n_check
+    return {'name': 'F4_ess', 'kind': 'ess', 'workload': 'SURVEY row f4: elliptical_slice updates of f for %d chains at N=%d on the device '
+            '(gpmc_ess_sweep)' % (B, n), 'n': n, 'chains': B, 'updates': updates, 'ms_per_update': ms,
+            'chain_updates_per_s': B / (ms * 1e-3), 'mean_proposals_per_update': trips / updates,
+            'gpu_vs_oracle': {'chains': n_check, 'trips_equal': bool(trips_equal), 'f_max_abs_err': worst,
+                              'cpu_oracle_s_per_update_incl_draw': cpu, 'how': 'nu, u, theta on a tape in the reference order'}}
+
+
 def sub_c1(gp, np, iters=30, cpu_iters=20, literal=False):
     """BASELINE config 1 (demoRegression.py: N=200, one chain): the reference's caller loop (demoRegression.py:23-30) on
     the drop-in `kcMCMC.sliceSample.surrogate_slice_sampling`, host arrays in / out, global numpy stream seeded like the
@@ -588,6 +668,10 @@ def run_b200(args):
                 if on('C3_sds'):
                     configs.append(sub_sds(gp, torch, np, 'C3_sds', 512, 4096, 4, 2, 0, peak_tf, 2,
                                            'BASELINE config 3: fused on-device slice loop, N=512, 4096 chains, ARD D=4'))
+                if on('F2_predict'):
+                    configs.append(sub_predict(gp, torch, np))
+                if on('F4_ess'):
+                    configs.append(sub_ess(gp, torch, np))
             if on('C5_sds'):
                 configs.append(sub_sds(gp, torch, np, 'C5_sds', n, 256, 0, 1, 0, peak_tf, 1 if world == 1 else 0,
                                        'BASELINE config 5 shard of the real sampler: N=%d, 256 chains per GPU, whole SDS '
