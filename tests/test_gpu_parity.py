@@ -564,3 +564,15 @@ def test_persistent_tile_kernel_is_bit_identical(gp, n, B):
             assert np.array_equal(ll, ref)
     finally:
         gp.ops.set_tuning(0, 4)
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 33])
+def test_tiny_matrices(gp, so, n):
+    """Orders below and around one 8x8 fragment / one 16-column pad: a single ragged panel with identity padding."""
+    x = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(3, n)
+    ll, info = gp.ops.loglik_host(x, G, H)
+    assert np.all(info == 0)
+    for b in range(3):
+        ref = so.loglik_unit(x, G[b], H[b], form='chol')
+        assert abs(ll[b] - ref) <= RTOL_LOGLIK * abs(ref)

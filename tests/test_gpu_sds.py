@@ -644,3 +644,27 @@ def test_large_n_resident_loop_repeats_bit_for_bit_by_default(gp):
     for r in runs[1:]:
         for a, b in zip(runs[0], r):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('n', [2, 5, 9])
+def test_sds_transition_at_tiny_n_matches_oracle(gp, n):
+    """Whole transitions for series of 2 .. 9 observations, tape-driven, against the oracle: proposal counts and theta'
+    exact."""
+    import torch
+    from oracle import sds_oracle as so
+    from oracle.reference_loader import Tape
+    B = 4
+    x, y = gp.synthetic.ih45_series(n)
+    F0, H0 = gp.synthetic.chain_states(B, n)
+    scale = np.array([10., 10., 5.])
+    tapes = [Tape.from_seed(70 + c, n, p=3, max_trips=64) for c in range(B)]
+    tp = gp.ops.Tape(np.stack([t.z for t in tapes]), np.stack([t.v for t in tapes]), [float(t.u0) for t in tapes],
+                     np.stack([t.U for t in tapes]))
+    F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
+    nt, ll, st = gp.ops.sds_sweep(x, y, F, H, scale, 1, tape=tp)
+    nt, Hn = nt.cpu().numpy(), H.cpu().numpy()
+    for c in range(B):
+        tr = so.SweepTrace()
+        of, oh = so.surrogate_slice_sampling(F0[c], x, y, H0[c], scale, 1, tapes[c], trace=tr, r_form='reduced')
+        assert int(nt[c]) == tr.n_trips
+        np.testing.assert_allclose(Hn[c], oh, rtol=1e-12)
