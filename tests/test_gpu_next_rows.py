@@ -352,3 +352,29 @@ def test_workspace_bounds_sds_predict_ess(gp, n, B, literal):
     F, H = torch.tensor(F0).cuda(), torch.tensor(H0).cuda()
     gp.ops.ess_sweep(x, y, F, H, it=1, seed=9, workspace=ws)
     ws.check()
+
+
+def test_empty_batches_and_invalid_hyperparameters(gp):
+    """Zero chains / zero stored samples are valid calls (empty results, no launch fails); a NaN length-scale or a negative
+    signal amplitude gives a NaN log-likelihood with info = -1 (the reference's jitchol raises / numpy propagates NaN),
+    the other items of the batch are unaffected."""
+    import torch
+    n = 40
+    x, y = gp.synthetic.ih45_series(n)
+    scale = np.array([10., 10., 5.])
+    F = torch.zeros((0, n), dtype=torch.float64, device='cuda')
+    H = torch.zeros((0, 3), dtype=torch.float64, device='cuda')
+    assert [tuple(t.shape) for t in gp.ops.sds_sweep(x, y, F, H, scale, 0, seed=1)] == [(0,), (0,), (0,)]
+    out = gp.ops.sds_run(x, y, F, H, scale, 0, 2, seed=1)
+    assert tuple(out[0].shape) == (0, 2, 3) and tuple(out[1].shape) == (0, 2)
+    xs = np.linspace(0, 10, 5).reshape(-1, 1)
+    assert [tuple(t.shape) for t in gp.ops.predict_batched(np.asarray(x).reshape(-1, 1), xs, F, H)] == [(0, 5), (0, 5), (0,)]
+    assert [tuple(t.shape) for t in gp.ops.ess_sweep(x, y, F, H, it=0, seed=1)] == [(0,), (0,), (0,)]
+    xx = np.arange(n, dtype=np.float64).reshape(n, 1)
+    G, Hh = gp.synthetic.loglik_batch(4, n)
+    good, _ = gp.ops.loglik_host(xx, G, Hh)
+    Hh[1, 0] = np.nan
+    Hh[3, 1] = -1.0
+    ll, info = gp.ops.loglik_host(xx, G, Hh)
+    assert np.isnan(ll[1]) and np.isnan(ll[3]) and info[1] != 0 and info[3] != 0
+    assert info[0] == 0 and info[2] == 0 and ll[0] == good[0] and ll[2] == good[2]
