@@ -378,3 +378,36 @@ def test_empty_batches_and_invalid_hyperparameters(gp):
     ll, info = gp.ops.loglik_host(xx, G, Hh)
     assert np.isnan(ll[1]) and np.isnan(ll[3]) and info[1] != 0 and info[3] != 0
     assert info[0] == 0 and info[2] == 0 and ll[0] == good[0] and ll[2] == good[2]
+
+
+def test_c_abi_rejects_bad_arguments_with_a_message(gp):
+    """Error behaviour of the C ABI on the device: too many ARD dimensions, a workspace smaller than one item, a leading
+    dimension that breaks the 16-element row alignment -- a non-zero code, a message from gpmc_last_error, no crash, and
+    the next valid call works."""
+    import torch
+    from gpmc_b200 import _lib
+    lib = _lib.load()
+    n = 64
+    x9 = np.random.RandomState(0).uniform(0, 5, size=(n, 9))
+    with pytest.raises(gp.GpmcError, match='MAX_ELL'):
+        gp.ops.cov_assemble(x9, np.ones((1, 11)))
+    # workspace too small
+    x = torch.arange(n, dtype=torch.float64, device='cuda').reshape(n, 1)
+    G, H = gp.synthetic.loglik_batch(2, n)
+    Gd, Hd = torch.tensor(G).cuda(), torch.tensor(H).cuda()
+    out = torch.empty(2, dtype=torch.float64, device='cuda')
+    info = torch.empty(2, dtype=torch.int32, device='cuda')
+    ws = torch.empty(1024, dtype=torch.uint8, device='cuda')
+    rc = lib.gpmc_loglik_batched(x.data_ptr(), n, 1, Gd.data_ptr(), Hd.data_ptr(), 2, 3, _lib.KIND_SE_ISO, gp.JITTER_PYGPS,
+                                 out.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc != 0 and len(lib.gpmc_last_error()) > 0
+    # misaligned leading dimension
+    A = torch.eye(n, dtype=torch.float64, device='cuda').reshape(1, n, n)[:, :, :n].contiguous()
+    bad = torch.zeros((1, n, n + 3), dtype=torch.float64, device='cuda')
+    inf2 = torch.empty(1, dtype=torch.int32, device='cuda')
+    wsb = torch.empty(1 << 20, dtype=torch.uint8, device='cuda')
+    rc = lib.gpmc_potrf_batched(bad.data_ptr(), n, n + 3, 1, inf2.data_ptr(), gp.JITTER_NONE, 1, wsb.data_ptr(), wsb.numel(), None)
+    assert rc != 0 and len(lib.gpmc_last_error()) > 0
+    # and the library is still usable
+    ll, inf = gp.ops.loglik_batched(x, Gd, Hd)
+    assert int((inf != 0).sum().item()) == 0 and bool(torch.isfinite(ll).all().item())
